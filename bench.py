@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: BASELINE.json's "Mandelbulb 4K samples/s".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one frame of BASELINE config 4: Mandelbulb power 8 (fragment.shd), frame buffer
+15360×8640 = 3840×2160 × 16 spp, lit by the prefiltered uffizi_512 environment maps,
+resolved in-kernel to 3840×2160 RGBA8.  Strong scaling: the frame's 8×8 tiles are dealt to
+the N ranks and gathered to rank 0 over NCCL.
+
+  value            samples/s with everything resident in HBM (CUDA events, max over ranks)
+  e2e              the same frame through the host-pointer C-ABI call: per step H2D of the five
+                   cube maps from pinned memory, kernel, (NCCL gather,) D2H of the resolved frame
+  roofline         FP32-FMA: algorithmic flop (device counters × SURVEY §8d constants) ÷ kernel
+                   time, against an in-run FFMA microbenchmark (MEASURED_PEAKS.json has no FP32
+                   number) — plus the HBM side to show the kernel is not bandwidth-bound
+  cpu_baseline     the CPU oracle (C restatement of the reference; llvmpipe/GHC are not in the
+                   image) on all host cores over a bounded sample of the same frame
+
+--impl reference times that CPU restatement alone (the reference itself — Haskell + GLSL —
+cannot be built here: no GHC, no OpenGL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# ---- workload: BASELINE.json configs[3] ---------------------------------------------------
+OUT_W, OUT_H, SPP_LOG2 = 3840, 2160, 2                   # 16 spp = 4×4 ordered grid
+FB_W, FB_H = OUT_W << SPP_LOG2, OUT_H << SPP_LOG2        # 15360 × 8640 samples
+SCENE_MB_POWER8 = 2
+TIME = 0.0
+WORKLOAD = "Mandelbulb power-8 3840x2160 x16spp (FB 15360x8640), prefiltered uffizi_512 env maps"
+
+# algorithmic FP32 flop constants, SURVEY.md §8d (GLSL-level count; transcendentals not counted)
+F_ITER, F_DE_TAIL, F_STEP, F_SAMPLE, F_HIT = 76.0, 9.0, 9.0, 55.0, 130.0
+
+
+def algorithmic_flops(c: dict) -> float:
+    de = c["march_de"] + c["shade_de"]
+    return (c["inner_iters"] * F_ITER + de * F_DE_TAIL + c["march_de"] * F_STEP +
+            c["samples"] * F_SAMPLE + c["hits"] * F_HIT)
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ---- environment maps (host side, product path: librmdf_b200 only) ------------------------
+def build_env_cubes(sr):
+    """uffizi_512.hdr → resize 256 → cos^{1,8,64,512} → RGBE → cube maps, all on the GPU through
+    the C ABI; returns the five face arrays (host, float32) for per-step uploads."""
+    import rmdf_b200 as R
+    refl = R.loadHDRImage(ROOT / "data" / "uffizi_512.hdr")
+    small = sr.resizeHDRImage(refl, 256)
+    conv = sr.cosineConvolveHDREnvMapSweep(small, sr.powers)
+    sr.latLongHDREnvMapToCubeMap(R.ENV_REFLECTION, refl)
+    for i in range(4):
+        sr.latLongHDREnvMapToCubeMap(R.ENV_COS_1 + i, sr.rgbeRoundTrip(conv[i]))
+    return [sr.getCubeMap(s) for s in range(5)]
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2])); power.append(float(t[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "power_w_max": float(max(power)), "samples": len(sm)}
+        return out
+
+
+# ---- CPU baseline (oracle; the only place bench.py touches oracle/) -----------------------
+def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = 12.0):
+    """Times the CPU restatement on a bounded, frame-covering sample of config 4: a 16×9 grid of
+    square crops spread uniformly over the 15360×8640 frame buffer, all host threads (OpenMP)."""
+    from oracle import oracle as O
+    img = O.hdr_decode((ROOT / "data" / "uffizi_512.hdr").read_bytes())
+    small = O.resize(img, 256)
+    envs = [O.latlong_to_cube(img)] + [O.latlong_to_cube(O.rgbe_roundtrip(O.convolve(small, p))) for p in (1.0, 8.0, 64.0, 512.0)]
+    cores = O.host_threads()
+
+    def run(crop):
+        n, t0 = 0, time.perf_counter()
+        for gy in range(9):
+            for gx in range(16):
+                cx = (FB_W // 16) * gx + FB_W // 32
+                cy = (FB_H // 9) * gy + FB_H // 18
+                x0, y0 = (cx - crop // 2) & ~1, (cy - crop // 2) & ~1
+                r = O.render(SCENE_MB_POWER8, FB_W, FB_H, TIME, envs=envs, rect=(x0, y0, x0 + crop, y0 + crop), want_linear=False)
+                n += r["counters"]["samples"]
+        return n, time.perf_counter() - t0
+
+    n, dt = run(64)                                   # probe, then size the sample to the budget
+    rate = n / dt
+    crop = int(min(960, max(64, ((rate * budget_s / 144.0) ** 0.5) // 2 * 2)))
+    for _ in range(warmup):
+        run(crop)
+    times, n = [], 0
+    for _ in range(max(1, steps)):
+        n, dt = run(crop)
+        times.append(dt)
+    dt = float(np.mean(times))
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "144 crops of %dx%d samples on a 16x9 grid over the 15360x8640 frame buffer (%.2f%% of the frame), "
+                      "C restatement of fragment.shd with OpenMP on all host threads — not llvmpipe/GHC (absent from the image)"
+                      % (crop, crop, 100.0 * n / (FB_W * FB_H)),
+            "seconds_per_step": dt, "samples_per_step": n}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    b = cpu_baseline_sample(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "mandelbulb_4k_samples_per_s", "value": b["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": b["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference": "CPU oracle port (reference = Haskell+GLSL, unbuildable here)"},
+            "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm -------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rmdf_b200 as R
+    from importlib import import_module
+    par = import_module("ray-marching-distance-fields_b200.parallel")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — librmdf_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    mode = R.MODE_FAST if args.mode == "fast" else R.MODE_PARITY
+
+    sr = R.ShaderRenderer(local)
+    cubes = build_env_cubes(sr)                              # host copies of the five cube maps
+    stream = torch.cuda.current_stream()
+    sr.setStream(stream.cuda_stream)
+
+    sharded = world > 1
+    p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
+                      shard_rank=rank if sharded else 0, shard_count=world if sharded else 1,
+                      layout=R.LAYOUT_PACKED_TILES if sharded else R.LAYOUT_FRAME)
+    n_out, n_tiles = sr.outputPixels(p)
+    out_dev = torch.empty(n_out, dtype=torch.int32, device=dev)
+    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (sharded and rank == 0) else None
+    frame_host = torch.empty(OUT_H * OUT_W, dtype=torch.int32).pin_memory() if rank == 0 else None
+    cubes_pinned = [torch.from_numpy(c).pin_memory() for c in cubes]
+    h2d_bytes = sum(c.numel() * 4 for c in cubes_pinned) + 64          # cube maps + rmdf_params
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        sr.renderDevice(p, out_dev.data_ptr())
+        if sharded:
+            dist.gather(out_dev, gather_list, dst=0)
+            if rank == 0:
+                return par.assemble_tiles_torch(torch.stack(gather_list), OUT_W, OUT_H, world)
+        return out_dev
+
+    def step_e2e():
+        for s, c in enumerate(cubes_pinned):                            # H2D: this step's inputs
+            R._capi.check(sr._lib.rmdf_envmap_bind_cube(sr.handle, s, c.data_ptr(), c.shape[1]))
+        if not sharded:
+            sr.renderHost(p, frame_host.data_ptr())                     # kernel + D2H through the C ABI
+        else:
+            frame = step_resident()
+            if rank == 0:
+                frame_host.copy_(frame.reshape(-1), non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            flush.zero_(); fn()
+        ms = []
+        barrier()
+        for _ in range(k):
+            flush.zero_()                                               # L2 flush, outside the events
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream); fn(); e1.record(stream)
+            barrier()
+            ms.append(max(e0.elapsed_time(e1), 0.0) if fn is step_resident else (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    sr.resetCounters()
+    l0 = sr.counters()["launches"]
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    c = sr.counters()
+    launches = (c["launches"] - l0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+
+    # per-launch kernel time and counters for the roofline (rank-local kernel, all ranks reduced)
+    per = args.steps + args.warmup
+    cnt = torch.tensor([c[k] / per for k in ("samples", "in_sphere", "hits", "march_de", "shade_de", "inner_iters")],
+                       dtype=torch.float64, device=dev)
+    kms = []
+    for _ in range(3):
+        flush.zero_(); sr.renderDevice(p, out_dev.data_ptr()); torch.cuda.synchronize()
+        kms.append(sr.counters()["last_kernel_ms"])
+    kt = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    frame_cnt = dict(zip(("samples", "in_sphere", "hits", "march_de", "shade_de", "inner_iters"), cnt.tolist()))
+    kernel_ms = float(kt.item())
+    fp32_peak = sr.measureFp32Peak() if rank == 0 else None
+
+    if rank == 0:
+        peaks, peaks_src = load_peaks()
+        flops = algorithmic_flops(frame_cnt)
+        samples = FB_W * FB_H
+        ach_tf = flops / (kernel_ms * 1e-3) / 1e12 / world               # per-GPU rate
+        alg_bytes = OUT_W * OUT_H * 4 + sum(c_.size * 2 // 3 * 4 // 4 for c_ in cubes)  # resolved frame + half4 texels
+        line = {
+            "metric": "mandelbulb_4k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scene": "FSMBPower8Shader", "in_time": TIME, "fb": [FB_W, FB_H], "out": [OUT_W, OUT_H],
+                       "spp": 1 << (2 * SPP_LOG2), "mode": args.mode, "parallelism": "tiles(tx+ty mod %d)" % world,
+                       "l2": "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"},
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4},
+            "gpu_launches": int(launches),
+            "sdf_steps_per_s": (frame_cnt["march_de"] + frame_cnt["shade_de"]) / (ms_res * 1e-3),
+            "frame_counters": {k: int(v) for k, v in frame_cnt.items()},
+            "roofline": {"bound": "fp32_fma", "achieved": ach_tf, "peak": fp32_peak["tflops"], "unit": "TFLOP/s",
+                         "frac": ach_tf / fp32_peak["tflops"], "traffic": None,
+                         "peak_source": "in-run FFMA-chain microbenchmark (%.0f MHz); MEASURED_PEAKS.json carries no FP32 figure" % fp32_peak["sm_mhz"],
+                         "algorithmic_flop_per_frame": flops, "kernel_ms": kernel_ms,
+                         "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            b = cpu_baseline_sample()
+            line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    sr.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

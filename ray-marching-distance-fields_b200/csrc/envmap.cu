@@ -1,0 +1,327 @@
+// envmap.cu — environment-map preprocessing kernels (compiled -fmad=false; FMAs are
+// written explicitly where they are wanted).
+//
+//   convolve_kernel   cosineConvolveHDREnvMap, HDREnvMap.hs:217-254  (the O(n^4) hot loop)
+//   resize_kernel     resizeHDRImage,          HDREnvMap.hs:169-195
+//   cube_kernel       latLongHDREnvMapToCubeMap, HDREnvMap.hs:118-163 (+ CoordTransf.hs)
+//   pack_half4_kernel the GL RGB16F upload,    HDREnvMap.hs:160-161
+//   mip_kernel        glGenerateMipmap chain,  FrameBuffer.hs:153-154
+//
+// Convolution design (FP32-FMA bound, ~28 instructions per (dst,src) pair, all four
+// powers from one cosine):
+//   * CTA = 32 destination columns × 8 destination rows; the 32×256 slice of the
+//     reference's per-pixel cos|φ_L−φ_x| lookup (HDREnvMap.hs:230) is computed ONCE
+//     on the host with the same libm calls and kept in 32 KB of shared memory, so
+//     `cosAngle` is bit-identical to the reference's and the `cosAngle > 0` sample
+//     count n matches exactly;
+//   * source rows are staged through shared memory as float4 (rgb·sinθ_P, pad) and
+//     read as 128-bit warp broadcasts;
+//   * powers {1,8,64,512} (ShaderRendering.hs:71) come from nine squarings of the
+//     cosine — no pow() in the loop (the reference's own TODO, HDREnvMap.hs:245-246);
+//   * the 128 source rows are split over gridDim.z CTAs; partial sums are reduced in
+//     a fixed order by a second tiny kernel (deterministic, no float atomics).
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+#include "rmdf_internal.h"
+
+namespace rmdf {
+
+constexpr int CV_DX = 32, CV_DY = 8, CV_THREADS = CV_DX * CV_DY;
+
+// tab: [dst_w][src_w] cos|φ_L − φ_x| ; cth/sth: cos/sin θ per row (host, libm)
+// partial: [splits][h*w][13]  (4 powers × rgb, n)
+template <bool CHAIN>
+__global__ void __launch_bounds__(CV_THREADS)
+convolve_kernel(const float *__restrict__ src, int w, int h, const float *__restrict__ tab,
+                const float *__restrict__ cth, const float *__restrict__ sth,
+                float p0, float p1, float p2, float p3, int np, int rows_per_split,
+                float *__restrict__ partial)
+{
+    extern __shared__ float smem[];
+    float *s_tab = smem;                                  // [w][CV_DX]  (transposed slice)
+    float4 *s_row = reinterpret_cast<float4 *>(smem + (size_t)w * CV_DX);   // [2][w]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int dstx = blockIdx.x * CV_DX + tx, dsty = blockIdx.y * CV_DY + ty;
+    const bool valid = dstx < w && dsty < h;
+
+    for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) {
+        const int sx = i / CV_DX, dx = blockIdx.x * CV_DX + (i % CV_DX);
+        s_tab[i] = (dx < w) ? tab[(size_t)dx * w + sx] : 0.0f;
+    }
+    const float lobe_cos = valid ? cth[dsty] : 0.0f, lobe_sin = valid ? sth[dsty] : 0.0f;
+    float acc[4][3];
+#pragma unroll
+    for (int p = 0; p < 4; p++) acc[p][0] = acc[p][1] = acc[p][2] = 0.0f;
+    float n = 0.0f;
+
+    const int y_begin = blockIdx.z * rows_per_split, y_end = min(h, y_begin + rows_per_split);
+    for (int y = y_begin; y < y_end; y++) {
+        float4 *row = s_row + (size_t)((y - y_begin) & 1) * w;
+        const float ps = sth[y];
+        for (int i = threadIdx.x; i < w; i += CV_THREADS) {
+            const float *s = src + ((size_t)y * w + i) * 3;
+            row[i] = make_float4(s[0] * ps, s[1] * ps, s[2] * ps, 0.0f);
+        }
+        __syncthreads();                                   // double-buffered: one barrier per row
+        const float a = __fmul_rn(lobe_cos, cth[y]);       // thetaLobeCos * thetaPxCos
+        const float b = __fmul_rn(lobe_sin, ps);           // thetaLobeSin * thetaPxSin
+#pragma unroll 4
+        for (int x = 0; x < w; x++) {
+            // cosAngle, HDREnvMap.hs:242-244, same rounding sequence as the reference
+            const float c = __fadd_rn(a, __fmul_rn(b, s_tab[x * CV_DX + tx]));
+            const float4 px = row[x];
+            const bool pos = c > 0.0f;
+            const float cc = pos ? c : 0.0f;
+            n += pos ? 1.0f : 0.0f;
+            if (CHAIN) {                                   // powers 1, 8, 64, 512
+                const float c2 = cc * cc, c4 = c2 * c2, c8 = c4 * c4;
+                const float c16 = c8 * c8, c32 = c16 * c16, c64 = c32 * c32;
+                const float c128 = c64 * c64, c256 = c128 * c128, c512 = c256 * c256;
+                acc[0][0] = __fmaf_rn(px.x, cc, acc[0][0]);   acc[0][1] = __fmaf_rn(px.y, cc, acc[0][1]);   acc[0][2] = __fmaf_rn(px.z, cc, acc[0][2]);
+                acc[1][0] = __fmaf_rn(px.x, c8, acc[1][0]);   acc[1][1] = __fmaf_rn(px.y, c8, acc[1][1]);   acc[1][2] = __fmaf_rn(px.z, c8, acc[1][2]);
+                acc[2][0] = __fmaf_rn(px.x, c64, acc[2][0]);  acc[2][1] = __fmaf_rn(px.y, c64, acc[2][1]);  acc[2][2] = __fmaf_rn(px.z, c64, acc[2][2]);
+                acc[3][0] = __fmaf_rn(px.x, c512, acc[3][0]); acc[3][1] = __fmaf_rn(px.y, c512, acc[3][1]); acc[3][2] = __fmaf_rn(px.z, c512, acc[3][2]);
+            } else {
+                const float pw[4] = { p0, p1, p2, p3 };
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    if (p < np) {
+                        const float cp = pos ? powf(c, pw[p]) : 0.0f;
+                        acc[p][0] = __fmaf_rn(px.x, cp, acc[p][0]);
+                        acc[p][1] = __fmaf_rn(px.y, cp, acc[p][1]);
+                        acc[p][2] = __fmaf_rn(px.z, cp, acc[p][2]);
+                    }
+                }
+            }
+        }
+    }
+    if (valid) {
+        float *o = partial + ((size_t)blockIdx.z * h * w + (size_t)dsty * w + dstx) * 13;
+#pragma unroll
+        for (int p = 0; p < 4; p++) { o[p * 3] = acc[p][0]; o[p * 3 + 1] = acc[p][1]; o[p * 3 + 2] = acc[p][2]; }
+        o[12] = n;
+    }
+}
+
+// out[p][y][x][c] = Σ_splits acc / Σ_splits n   ("divide sum by number of hemisphere samples", :231-232)
+__global__ void convolve_finish_kernel(const float *__restrict__ partial, int npix, int splits, int np, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float acc[12], n = 0.0f;
+    for (int k = 0; k < 12; k++) acc[k] = 0.0f;
+    for (int s = 0; s < splits; s++) {
+        const float *p = partial + ((size_t)s * npix + i) * 13;
+        for (int k = 0; k < 12; k++) acc[k] += p[k];
+        n += p[12];
+    }
+    for (int p = 0; p < np; p++)
+        for (int c = 0; c < 3; c++) out[((size_t)p * npix + i) * 3 + c] = acc[p * 3 + c] / n;
+}
+
+// Host-side tables, same libm calls and rounding as HDREnvMap.hs:223-236.
+static void convolve_tables(int w, int h, float *tab, float *cth, float *sth)
+{
+    const float pi = 3.14159265358979323846f;
+    for (int y = 0; y < h; y++) {
+        const float theta = (float)y / (float)(h - 1) * pi;
+        cth[y] = cosf(theta);
+        sth[y] = sinf(theta);
+    }
+    for (int dx = 0; dx < w; dx++) {
+        const float phi_lobe = (float)dx / (float)(w - 1) * 2.0f * pi;
+        for (int sx = 0; sx < w; sx++)
+            tab[(size_t)dx * w + sx] = cosf(fabsf(phi_lobe - (float)sx / (float)(w - 1) * 2.0f * pi));
+    }
+}
+
+cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_host, int np,
+                            float *out_dev, cudaStream_t s)
+{
+    cudaError_t e;
+    const size_t ntab = (size_t)w * w;
+    float *host = (float *)malloc(sizeof(float) * (ntab + 2 * (size_t)h));
+    if (!host) return cudaErrorMemoryAllocation;
+    convolve_tables(w, h, host, host + ntab, host + ntab + h);
+    float *d_tab = nullptr, *d_partial = nullptr;
+    const int splits = 4, rows_per_split = (h + splits - 1) / splits;
+    const size_t npix = (size_t)w * h;
+    if ((e = cudaMallocAsync(&d_tab, sizeof(float) * (ntab + 2 * (size_t)h), s)) != cudaSuccess) { free(host); return e; }
+    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * splits * npix * 13, s)) != cudaSuccess) { cudaFreeAsync(d_tab, s); free(host); return e; }
+    e = cudaMemcpyAsync(d_tab, host, sizeof(float) * (ntab + 2 * (size_t)h), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // host table is freed below
+    free(host);
+    const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
+    const dim3 grid((w + CV_DX - 1) / CV_DX, (h + CV_DY - 1) / CV_DY, splits);
+    for (int first = 0; first < np && e == cudaSuccess; first += 4) {
+        const int cnt = (np - first < 4) ? np - first : 4;
+        float p[4] = { 0, 0, 0, 0 };
+        for (int k = 0; k < cnt; k++) p[k] = powers_host[first + k];
+        const bool chain = cnt == 4 && p[0] == 1.0f && p[1] == 8.0f && p[2] == 64.0f && p[3] == 512.0f;
+        if (chain) {
+            cudaFuncSetAttribute(convolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            convolve_kernel<true><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
+                                                                 p[0], p[1], p[2], p[3], cnt, rows_per_split, d_partial);
+        } else {
+            cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            convolve_kernel<false><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
+                                                                  p[0], p[1], p[2], p[3], cnt, rows_per_split, d_partial);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        convolve_finish_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(d_partial, (int)npix, splits, cnt, out_dev + (size_t)first * npix * 3);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(d_tab, s);
+    cudaFreeAsync(d_partial, s);
+    return e;
+}
+
+// ---- pixelAtBilinear, HDREnvMap.hs:91-113 ------------------------------------------------
+__device__ __forceinline__ void pixel_at_bilinear(const float *img, int w, int h, float u, float v, float out[3])
+{
+    const float upx = u * ((float)w - 1.0f), upy = v * ((float)h - 1.0f);
+    const int x = (int)floorf(upx), y = (int)floorf(upy);
+    const int xp1 = (x + 1) % (w - 1);                       // sic: mod (w-1), :100
+    const int yp1 = min(h - 1, y + 1);
+    const float ur = upx - (float)x, vr = upy - (float)y, uo = 1.0f - ur, vo = 1.0f - vr;
+    const float *t00 = img + ((size_t)y * w + x) * 3, *t10 = img + ((size_t)y * w + xp1) * 3;
+    const float *t01 = img + ((size_t)yp1 * w + x) * 3, *t11 = img + ((size_t)yp1 * w + xp1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        out[c] = (t00[c] * uo + t10[c] * ur) * vo + (t01[c] * uo + t11[c] * ur) * vr;
+}
+
+// ---- resizeHDRImage, HDREnvMap.hs:169-195 (IEEE ops only: bit-identical to the oracle) ----
+__global__ void resize_kernel(const float *__restrict__ src, int srcw, int srch, int dstw, int dsth, float *__restrict__ dst)
+{
+    const int dstx = blockIdx.x * blockDim.x + threadIdx.x, dsty = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dstx >= dstw || dsty >= dsth) return;
+    const float scale = (float)srcw / (float)dstw;
+    const int taps = (int)ceilf(scale);
+    const float ntaps = (float)(taps * taps), step = scale / (float)taps;
+    const float srcx1 = (float)dstx * scale, srcy1 = (float)dsty * scale;
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
+    for (int ty = 0; ty < taps; ty++)
+        for (int tx = 0; tx < taps; tx++) {
+            const float srcx = srcx1 + (float)tx * step, srcy = srcy1 + (float)ty * step;
+            float p[3];
+            pixel_at_bilinear(src, srcw, srch, srcx / ((float)srcw - 1.0f), srcy / ((float)srch - 1.0f), p);
+            acc[0] = acc[0] + p[0]; acc[1] = acc[1] + p[1]; acc[2] = acc[2] + p[2];
+        }
+    float *o = dst + ((size_t)dsty * dstw + dstx) * 3;
+    o[0] = acc[0] / ntaps; o[1] = acc[1] / ntaps; o[2] = acc[2] / ntaps;
+}
+cudaError_t launch_resize(const float *src_dev, int w, int h, int dstw, int dsth, float *out_dev, cudaStream_t s)
+{
+    const dim3 block(32, 8), grid((dstw + 31) / 32, (dsth + 7) / 8);
+    resize_kernel<<<grid, block, 0, s>>>(src_dev, w, h, dstw, dsth, out_dev);
+    return cudaGetLastError();
+}
+
+// ---- latLongHDREnvMapToCubeMap, HDREnvMap.hs:118-163 ---------------------------------------
+__global__ void cube_kernel(const float *__restrict__ latlong, int w, int h, int fw, float *__restrict__ faces)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, face = blockIdx.z;
+    if (x >= fw || y >= fw) return;
+    const float pi = 3.14159265358979323846f;
+    // cubeMapPixelToDir, :76-87
+    const float vw = ((float)x + 0.5f) / (float)fw * 2.0f - 1.0f;
+    const float vh = ((float)y + 0.5f) / (float)fw * 2.0f - 1.0f;
+    float d0, d1, d2;
+    switch (face) {
+    case 0:  d0 = 1.0f;  d1 = -vh;   d2 = -vw;   break;
+    case 1:  d0 = -1.0f; d1 = -vh;   d2 = vw;    break;
+    case 2:  d0 = vw;    d1 = 1.0f;  d2 = vh;    break;
+    case 3:  d0 = vw;    d1 = -1.0f; d2 = -vh;   break;
+    case 4:  d0 = vw;    d1 = -vh;   d2 = 1.0f;  break;
+    default: d0 = -vw;   d1 = -vh;   d2 = -1.0f; break;
+    }
+    // linear's normalize: unchanged when |l| or |1-l| <= 1e-6
+    const float l = (d0 * d0 + d1 * d1) + d2 * d2;
+    if (!(fabsf(l) <= 1e-6f || fabsf(1.0f - l) <= 1e-6f)) {
+        const float s = sqrtf(l);
+        d0 = d0 / s; d1 = d1 / s; d2 = d2 / s;
+    }
+    // worldToLocal (CoordTransf.hs:47-51): (x, -z, y); cartesianToSpherical (:35-45)
+    const float lx = d0, ly = -d2, lz = d1;
+    const float theta = acosf(fmaxf(-1.0f, fminf(1.0f, lz)));
+    float phi = atan2f(ly, lx);
+    if (phi < 0.0f) phi = phi + 2.0f * pi;
+    if (phi == 2.0f * pi) phi = 0.0f;
+    // sphericalToEnvironmentUV (:61-71)
+    const float p1 = phi + pi / 2.0f;
+    const float p2 = (p1 > 2.0f * pi) ? p1 - 2.0f * pi : p1;
+    const float p3 = 2.0f * pi - p2;
+    float col[3];
+    pixel_at_bilinear(latlong, w, h, p3 / (pi * 2.0f), theta / pi, col);
+    float *o = faces + (((size_t)face * fw + y) * fw + x) * 3;
+    // GL converts to half on upload (RGB16F, :160-161); keep the rounded value as float
+    o[0] = __half2float(__float2half_rn(col[0]));
+    o[1] = __half2float(__float2half_rn(col[1]));
+    o[2] = __half2float(__float2half_rn(col[2]));
+}
+cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int face_w, float *faces_dev, cudaStream_t s)
+{
+    const dim3 block(32, 8), grid((face_w + 31) / 32, (face_w + 7) / 8, 6);
+    cube_kernel<<<grid, block, 0, s>>>(latlong_dev, w, h, face_w, faces_dev);
+    return cudaGetLastError();
+}
+
+// float RGB faces → half4 texels (CUDA has no 3-channel half format); also rounds to half
+__global__ void pack_half4_kernel(float *__restrict__ faces, int n, ushort4 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const __half r = __float2half_rn(faces[i * 3]), g = __float2half_rn(faces[i * 3 + 1]), b = __float2half_rn(faces[i * 3 + 2]);
+    faces[i * 3] = __half2float(r); faces[i * 3 + 1] = __half2float(g); faces[i * 3 + 2] = __half2float(b);
+    out[i] = make_ushort4(__half_as_ushort(r), __half_as_ushort(g), __half_as_ushort(b), 0x3c00 /* 1.0 */);
+}
+cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s)
+{
+    const int n = 6 * face_w * face_w;
+    pack_half4_kernel<<<(n + 255) / 256, 256, 0, s>>>(const_cast<float *>(faces_dev), n, reinterpret_cast<ushort4 *>(half4_dev));
+    return cudaGetLastError();
+}
+
+// ---- glGenerateMipmap box chain, one level per launch ---------------------------------------
+__device__ __forceinline__ uint32_t mip_box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    uint32_t lo = (a & 0x00ff00ffu) + (b & 0x00ff00ffu) + (c & 0x00ff00ffu) + (d & 0x00ff00ffu) + 0x00020002u;
+    uint32_t hi = ((a >> 8) & 0x00ff00ffu) + ((b >> 8) & 0x00ff00ffu) + ((c >> 8) & 0x00ff00ffu) + ((d >> 8) & 0x00ff00ffu) + 0x00020002u;
+    return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
+}
+__global__ void mip_kernel(const uint32_t *__restrict__ in, int w, int nw, int nh, uint32_t *__restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nw || y >= nh) return;
+    const uint32_t *p = in + (size_t)(2 * y) * w + 2 * x;
+    out[(size_t)y * nw + x] = mip_box4(p[0], p[1], p[w], p[w + 1]);
+}
+cudaError_t launch_mip_resolve(const uint32_t *in_dev, int w, int h, int levels, uint32_t *out_dev, cudaStream_t s)
+{
+    if (levels == 0) return cudaMemcpyAsync(out_dev, in_dev, sizeof(uint32_t) * (size_t)w * h, cudaMemcpyDeviceToDevice, s);
+    uint32_t *tmp[2] = { nullptr, nullptr };
+    cudaError_t e = cudaSuccess;
+    const uint32_t *cur = in_dev;
+    for (int l = 0; l < levels && e == cudaSuccess; l++) {
+        const int nw = w >> 1, nh = h >> 1;
+        uint32_t *dst = out_dev;
+        if (l != levels - 1) {
+            if (!tmp[l & 1]) e = cudaMallocAsync(&tmp[l & 1], sizeof(uint32_t) * (size_t)nw * nh, s);
+            if (e != cudaSuccess) break;
+            dst = tmp[l & 1];
+        }
+        const dim3 block(32, 8), grid((nw + 31) / 32, (nh + 7) / 8);
+        mip_kernel<<<grid, block, 0, s>>>(cur, w, nw, nh, dst);
+        e = cudaGetLastError();
+        cur = dst; w = nw; h = nh;
+    }
+    if (tmp[0]) cudaFreeAsync(tmp[0], s);
+    if (tmp[1]) cudaFreeAsync(tmp[1], s);
+    return e;
+}
+
+}  // namespace rmdf

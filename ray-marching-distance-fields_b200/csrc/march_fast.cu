@@ -1,0 +1,28 @@
+// march_fast.cu — fast build of the march kernel.
+// Compiled with --use_fast_math (FMA contraction, MUFU sqrt/rsqrt/rcp/lg2/ex2/sin/cos,
+// flush-to-zero) and hardware seamless cube-map filtering.  Not bit-identical to the
+// oracle: its distance from the parity build is measured against the intrinsic noise
+// floor of the eps = 1e-5 normal in tests/test_march_parity.py.
+#include "march_kernel.cuh"
+
+namespace rmdf {
+
+struct MathFast {
+    static constexpr bool kFast = true;
+    static constexpr int  kMinCtas = 2;
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float inversesqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return (x > 0.0f) ? __powf(x, y) : ((x != x) ? x : 0.0f); }
+    static __device__ __forceinline__ float sin(float x) { return sinf(x); }
+    static __device__ __forceinline__ float cos(float x) { return cosf(x); }
+    static __device__ __forceinline__ float acos(float x) { return acosf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+};
+
+cudaError_t launch_march_fast(const MarchParams &p, int grid, cudaStream_t s) { return launch_march_impl<MathFast>(p, grid, s); }
+int march_fast_ctas_per_sm(int scene) { return march_ctas_per_sm_impl<MathFast>(scene); }
+
+}  // namespace rmdf

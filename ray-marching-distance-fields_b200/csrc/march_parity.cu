@@ -1,0 +1,27 @@
+// march_parity.cu — parity build of the march kernel.
+// Compiled with -fmad=false: every FP32 operation is an individually rounded IEEE
+// add/mul/div/sqrt, and all GLSL built-ins come from include/rmdf_glsl.h, so the
+// kernel's output is bit-identical to the CPU oracle's (tests/test_march_parity.py).
+#include "march_kernel.cuh"
+
+namespace rmdf {
+
+struct MathParity {
+    static constexpr bool kFast = false;
+    static constexpr int  kMinCtas = 2;
+    static __device__ __forceinline__ float sqrt(float x) { return rg_sqrt(x); }
+    static __device__ __forceinline__ float inversesqrt(float x) { return rg_inversesqrt(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+    static __device__ __forceinline__ float log(float x) { return rg_log(x); }
+    static __device__ __forceinline__ float exp(float x) { return rg_exp(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return rg_pow(x, y); }
+    static __device__ __forceinline__ float sin(float x) { return rg_sin(x); }
+    static __device__ __forceinline__ float cos(float x) { return rg_cos(x); }
+    static __device__ __forceinline__ float acos(float x) { return rg_acos(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return rg_atan2(y, x); }
+};
+
+cudaError_t launch_march_parity(const MarchParams &p, int grid, cudaStream_t s) { return launch_march_impl<MathParity>(p, grid, s); }
+int march_parity_ctas_per_sm(int scene) { return march_ctas_per_sm_impl<MathParity>(scene); }
+
+}  // namespace rmdf

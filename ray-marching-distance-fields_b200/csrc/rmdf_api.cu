@@ -1,0 +1,720 @@
+// rmdf_api.cu — the C ABI of librmdf_b200.so (include/rmdf.h): context lifetime,
+// env-map texture objects, parameter validation, work-list construction, launches.
+// Host arithmetic that must agree bit-for-bit with the kernels' inputs (camera,
+// Cornell triangle terms) uses include/rmdf_glsl.h and is compiled with
+// -Xcompiler -ffp-contract=off.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <math.h>
+#include <mutex>
+#include <vector>
+#include "../../include/rmdf.h"
+#include "../../include/rmdf_glsl.h"
+#include "rmdf_internal.h"
+
+using namespace rmdf;
+
+// ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(RMDF_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct EnvSlot {
+    int face_w = 0;
+    cudaArray_t arr_layered = nullptr, arr_cube = nullptr;
+    cudaTextureObject_t tex_point = 0, tex_cube = 0;
+    float *faces_dev = nullptr;        // 6·w·w·3 half-rounded floats (for rmdf_envmap_get_cube)
+};
+
+struct rmdf_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    unsigned int *d_queue = nullptr;
+    unsigned long long *d_counters = nullptr;
+    uint64_t launches = 0;
+    EnvSlot env[RMDF_ENV_SLOTS];
+    float4 *d_cornell = nullptr;
+    bool have_cornell = false;
+    void *d_out = nullptr;             // staging for the host-pointer entry points
+    size_t d_out_bytes = 0;
+    std::recursive_mutex mu;
+};
+
+static int use(rmdf_ctx *ctx)
+{
+    if (!ctx) return fail(RMDF_ERR_ARG, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    return RMDF_OK;
+}
+static int ensure_staging(rmdf_ctx *ctx, size_t bytes)
+{
+    if (ctx->d_out_bytes >= bytes) return RMDF_OK;
+    if (ctx->d_out) { cudaFree(ctx->d_out); ctx->d_out = nullptr; ctx->d_out_bytes = 0; }
+    CU(cudaMalloc(&ctx->d_out, bytes));
+    ctx->d_out_bytes = bytes;
+    return RMDF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+extern "C" const char *rmdf_last_error(void) { return g_err; }
+extern "C" int rmdf_abi_version(void) { return RMDF_ABI_VERSION; }
+
+extern "C" int rmdf_create(rmdf_ctx **out, int device)
+{
+    if (!out) return fail(RMDF_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RMDF_ERR_CUDA, "no CUDA device: %s (librmdf_b200 has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(RMDF_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RMDF_ERR_CUDA, "device %d is sm_%d%d; librmdf_b200 carries sm_100a code only", device, prop.major, prop.minor);
+    rmdf_ctx *ctx = new rmdf_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t err = cudaSuccess;
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev0);
+    if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev1);
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_queue, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * C_NSLOTS);
+    if (err == cudaSuccess) err = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS);
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_cornell, sizeof(float4) * kCornellF4);
+    if (err != cudaSuccess) {
+        fail(RMDF_ERR_CUDA, "rmdf_create: %s", cudaGetErrorString(err));
+        rmdf_destroy(ctx);
+        return RMDF_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return RMDF_OK;
+}
+
+static void free_slot(EnvSlot &s)
+{
+    if (s.tex_point) cudaDestroyTextureObject(s.tex_point);
+    if (s.tex_cube) cudaDestroyTextureObject(s.tex_cube);
+    if (s.arr_layered) cudaFreeArray(s.arr_layered);
+    if (s.arr_cube) cudaFreeArray(s.arr_cube);
+    if (s.faces_dev) cudaFree(s.faces_dev);
+    s = EnvSlot();
+}
+
+extern "C" void rmdf_destroy(rmdf_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < RMDF_ENV_SLOTS; i++) free_slot(ctx->env[i]);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_cornell) cudaFree(ctx->d_cornell);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_queue) cudaFree(ctx->d_queue);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" int rmdf_set_stream(rmdf_ctx *ctx, void *cuda_stream)
+{
+    int rc = use(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RMDF_OK;
+}
+extern "C" int rmdf_sync(rmdf_ctx *ctx)
+{
+    int rc = use(ctx); if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RMDF_OK;
+}
+
+// ---- env maps ---------------------------------------------------------------------
+extern "C" int rmdf_envmap_resize_height(int w, int h, int dstw)
+{
+    if (w <= 0 || h <= 0 || dstw <= 0) return 0;
+    return (int)rintf((float)h / (float)w * (float)dstw);      // Haskell `round`: half to even
+}
+
+extern "C" int rmdf_envmap_resize(rmdf_ctx *ctx, const float *rgb, int w, int h, int dstw, float *out)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!rgb || !out || w < 2 || h < 2 || dstw < 1) return fail(RMDF_ERR_ARG, "rmdf_envmap_resize: bad image %dx%d -> %d", w, h, dstw);
+    const int dsth = rmdf_envmap_resize_height(w, h, dstw);
+    if (dsth < 1) return fail(RMDF_ERR_ARG, "rmdf_envmap_resize: target height is 0");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    float *d_src = nullptr, *d_dst = nullptr;
+    const size_t nsrc = sizeof(float) * 3 * (size_t)w * h, ndst = sizeof(float) * 3 * (size_t)dstw * dsth;
+    CU(cudaMalloc(&d_src, nsrc));
+    cudaError_t e = cudaMalloc(&d_dst, ndst);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, rgb, nsrc, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_resize(d_src, w, h, dstw, dsth, d_dst, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(out, d_dst, ndst, cudaMemcpyDeviceToHost, ctx->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_src); if (d_dst) cudaFree(d_dst);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_resize: %s", cudaGetErrorString(e));
+    return RMDF_OK;
+}
+
+static int convolve_check(const void *rgb, int w, int h, const float *powers, int np, const void *out)
+{
+    if (!rgb || !out || !powers) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: NULL pointer");
+    if (w < 2 || h < 2 || w > 1024) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: image %dx%d unsupported (2 <= w <= 1024)", w, h);
+    if (np < 1 || np > 64) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: np = %d out of range [1,64]", np);
+    return RMDF_OK;
+}
+extern "C" int rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
+                                           const float *powers, int np, void *out_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if ((rc = convolve_check(rgb_dev, w, h, powers, np, out_dev))) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = launch_convolve((const float *)rgb_dev, w, h, powers, np, (float *)out_dev, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_convolve: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->launches += 2 * (uint64_t)((np + 3) / 4);
+    return RMDF_OK;
+}
+extern "C" int rmdf_envmap_convolve(rmdf_ctx *ctx, const float *rgb, int w, int h,
+                                    const float *powers, int np, float *out)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if ((rc = convolve_check(rgb, w, h, powers, np, out))) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    float *d_src = nullptr, *d_dst = nullptr;
+    const size_t nsrc = sizeof(float) * 3 * (size_t)w * h;
+    CU(cudaMalloc(&d_src, nsrc));
+    cudaError_t e = cudaMalloc(&d_dst, nsrc * np);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, rgb, nsrc, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rc = rmdf_envmap_convolve_device(ctx, d_src, w, h, powers, np, d_dst);
+        if (rc == RMDF_OK) e = cudaMemcpyAsync(out, d_dst, nsrc * np, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_src); if (d_dst) cudaFree(d_dst);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_convolve: %s", cudaGetErrorString(e));
+    return RMDF_OK;
+}
+
+// JuicyPixels RGBE convention (Codec.Picture.HDR toRGBE / toFloat; not vendored in the
+// reference — see DESIGN.md "third-party arithmetic").
+extern "C" int rmdf_rgbe_roundtrip(float *rgb, int64_t npix)
+{
+    if (!rgb || npix < 0) return fail(RMDF_ERR_ARG, "rmdf_rgbe_roundtrip: bad arguments");
+    for (int64_t i = 0; i < npix; i++) {
+        float *p = rgb + i * 3;
+        float d = p[0];
+        if (p[1] > d) d = p[1];
+        if (p[2] > d) d = p[2];
+        if (d <= 1e-32f) { p[0] = p[1] = p[2] = 0.0f; continue; }
+        int e;
+        const float sig = frexpf(d, &e);
+        const float coeff = sig * 255.9999f / d;
+        const float f = ldexpf(1.0f, (e + 128) - (128 + 8));
+        for (int c = 0; c < 3; c++) {
+            const int m = (int)(unsigned char)(int)truncf(p[c] * coeff);
+            p[c] = ((float)m + 0.0f) * f;
+        }
+    }
+    return RMDF_OK;
+}
+
+static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *faces_dev_src)
+{
+    // faces_dev_src: 6·fw·fw·3 floats already on the device (ownership moves to the slot)
+    cudaStream_t st = ctx->stream;
+    const size_t ntex = (size_t)6 * fw * fw;
+    void *d_half4 = nullptr;
+    CU(cudaMalloc(&d_half4, ntex * 8));
+    cudaError_t e = launch_pack_half4(faces_dev_src, fw, d_half4, st);
+    ctx->launches++;
+    const cudaChannelFormatDesc desc = cudaCreateChannelDescHalf4();
+    const cudaExtent ext = make_cudaExtent((size_t)fw, (size_t)fw, 6);
+    if (e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_layered, &desc, ext, cudaArrayLayered);
+    if (e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_cube, &desc, ext, cudaArrayCubemap);
+    for (int which = 0; which < 2 && e == cudaSuccess; which++) {
+        cudaMemcpy3DParms cp;
+        memset(&cp, 0, sizeof cp);
+        cp.srcPtr = make_cudaPitchedPtr(d_half4, (size_t)fw * 8, (size_t)fw, (size_t)fw);
+        cp.dstArray = which ? s.arr_cube : s.arr_layered;
+        cp.extent = ext;
+        cp.kind = cudaMemcpyDeviceToDevice;
+        e = cudaMemcpy3DAsync(&cp, st);
+    }
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray;
+        cudaTextureDesc td; memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.readMode = cudaReadModeElementType;
+        // exact texel fetch for the parity path (FP32 weights are applied in the kernel)
+        rd.res.array.array = s.arr_layered;
+        td.filterMode = cudaFilterModePoint; td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&s.tex_point, &rd, &td, nullptr);
+        if (e == cudaSuccess) {
+            // GL_TEXTURE_CUBE_MAP_SEAMLESS + LINEAR (HDREnvMap.hs:122-126) for the fast path
+            rd.res.array.array = s.arr_cube;
+            td.filterMode = cudaFilterModeLinear; td.normalizedCoords = 1; td.seamlessCubemap = 1;
+            e = cudaCreateTextureObject(&s.tex_cube, &rd, &td, nullptr);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_half4);
+    if (e != cudaSuccess) {
+        free_slot(s);
+        return fail(RMDF_ERR_CUDA, "env-map texture setup: %s", cudaGetErrorString(e));
+    }
+    s.face_w = fw;
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
+    if (!faces_rgb || face_w < 1 || face_w > 8192) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind_cube: bad faces (w = %d)", face_w);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_slot(ctx->env[slot]);
+    EnvSlot &s = ctx->env[slot];
+    const size_t bytes = sizeof(float) * 3 * 6 * (size_t)face_w * face_w;
+    CU(cudaMalloc(&s.faces_dev, bytes));
+    cudaError_t e = cudaMemcpyAsync(s.faces_dev, faces_rgb, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { free_slot(s); return fail(RMDF_ERR_CUDA, "rmdf_envmap_bind_cube: %s", cudaGetErrorString(e)); }
+    return make_slot_textures(ctx, s, face_w, s.faces_dev);
+}
+
+extern "C" int rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rgb, int w, int h)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
+    if (!latlong_rgb || w < 3 || h < 2) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind: bad image %dx%d", w, h);
+    const int fw = w / 3;                                    // HDREnvMap.hs:128
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_slot(ctx->env[slot]);
+    EnvSlot &s = ctx->env[slot];
+    float *d_ll = nullptr;
+    const size_t nll = sizeof(float) * 3 * (size_t)w * h;
+    CU(cudaMalloc(&d_ll, nll));
+    cudaError_t e = cudaMalloc(&s.faces_dev, sizeof(float) * 3 * 6 * (size_t)fw * fw);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ll, latlong_rgb, nll, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_latlong_to_cube(d_ll, w, h, fw, s.faces_dev, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ll);
+    if (e != cudaSuccess) { free_slot(s); return fail(RMDF_ERR_CUDA, "rmdf_envmap_bind: %s", cudaGetErrorString(e)); }
+    return make_slot_textures(ctx, s, fw, s.faces_dev);
+}
+
+extern "C" int rmdf_envmap_get_cube(rmdf_ctx *ctx, int slot, float *faces_rgb, int *face_w)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    const EnvSlot &s = ctx->env[slot];
+    if (face_w) *face_w = s.face_w;
+    if (faces_rgb && s.face_w > 0) {
+        CU(cudaMemcpyAsync(faces_rgb, s.faces_dev, sizeof(float) * 3 * 6 * (size_t)s.face_w * s.face_w, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_envmap_unbind(rmdf_ctx *ctx, int slot)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_slot(ctx->env[slot]);
+    return RMDF_OK;
+}
+
+// ---- Cornell geometry --------------------------------------------------------------
+// CornellBox.hs:48-129 (quads) and :26-38 (triangulation, centring, scaling)
+static const float kCornellQuads[64][3] = {
+    {552.8f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 559.2f}, {549.6f, 0.0f, 559.2f},
+    {556.0f, 548.8f, 0.0f}, {556.0f, 548.8f, 559.2f}, {0.0f, 548.8f, 559.2f}, {0.0f, 548.8f, 0.0f},
+    {549.6f, 0.0f, 559.2f}, {0.0f, 0.0f, 559.2f}, {0.0f, 548.8f, 559.2f}, {556.0f, 548.8f, 559.2f},
+    {0.0f, 0.0f, 559.2f}, {0.0f, 0.0f, 0.0f}, {0.0f, 548.8f, 0.0f}, {0.0f, 548.8f, 559.2f},
+    {552.8f, 0.0f, 0.0f}, {549.6f, 0.0f, 559.2f}, {556.0f, 548.8f, 559.2f}, {556.0f, 548.8f, 0.0f},
+    {343.0f, -1.0f, 227.0f}, {343.0f, -1.0f, 332.0f}, {213.0f, -1.0f, 332.0f}, {213.0f, -1.0f, 227.0f},
+    {130.0f, 165.0f, 65.0f}, {82.0f, 165.0f, 225.0f}, {240.0f, 165.0f, 272.0f}, {290.0f, 165.0f, 114.0f},
+    {290.0f, 0.0f, 114.0f}, {290.0f, 165.0f, 114.0f}, {240.0f, 165.0f, 272.0f}, {240.0f, 0.0f, 272.0f},
+    {130.0f, 0.0f, 65.0f}, {130.0f, 165.0f, 65.0f}, {290.0f, 165.0f, 114.0f}, {290.0f, 0.0f, 114.0f},
+    {82.0f, 0.0f, 225.0f}, {82.0f, 165.0f, 225.0f}, {130.0f, 165.0f, 65.0f}, {130.0f, 0.0f, 65.0f},
+    {240.0f, 0.0f, 272.0f}, {240.0f, 165.0f, 272.0f}, {82.0f, 165.0f, 225.0f}, {82.0f, 0.0f, 225.0f},
+    {423.0f, 330.0f, 247.0f}, {265.0f, 330.0f, 296.0f}, {314.0f, 330.0f, 456.0f}, {472.0f, 330.0f, 406.0f},
+    {423.0f, 0.0f, 247.0f}, {423.0f, 330.0f, 247.0f}, {472.0f, 330.0f, 406.0f}, {472.0f, 0.0f, 406.0f},
+    {472.0f, 0.0f, 406.0f}, {472.0f, 330.0f, 406.0f}, {314.0f, 330.0f, 456.0f}, {314.0f, 0.0f, 456.0f},
+    {314.0f, 0.0f, 456.0f}, {314.0f, 330.0f, 456.0f}, {265.0f, 330.0f, 296.0f}, {265.0f, 0.0f, 296.0f},
+    {265.0f, 0.0f, 296.0f}, {265.0f, 330.0f, 296.0f}, {423.0f, 330.0f, 247.0f}, {423.0f, 0.0f, 247.0f},
+};
+extern "C" int rmdf_cornell_box_vertices(float *xyz)
+{
+    if (!xyz) return fail(RMDF_ERR_ARG, "rmdf_cornell_box_vertices: NULL");
+    const float to_unit = 559.2f / 2.0f;
+    const float scale = 1.0f / (sqrtf(2.0f * 2.0f + 2.0f * 2.0f + 2.0f * 2.0f) / 2.0f) * 0.99f;
+    static const int corner[6] = { 0, 1, 3, 3, 1, 2 };
+    int n = 0;
+    for (int q = 0; q < 16; q++)
+        for (int k = 0; k < 6; k++)
+            for (int c = 0; c < 3; c++) {
+                float v = kCornellQuads[q * 4 + corner[k]][c];
+                if (v == -1.0f) v = 548.8f - 0.1f;              // light, CornellBox.hs:81-84
+                xyz[n++] = (v / to_unit - 1.0f) * scale;
+            }
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!xyz || nverts != 96) return fail(RMDF_ERR_ARG, "rmdf_set_cornell: expected 96 vertices, got %d", nverts);
+    // position-independent terms of compute_barycentric / line_seg_min_dist_sq
+    // (fragment.shd:312-346), same operation order as the shader
+    float4 tab[kCornellF4];
+    for (int i = 0; i < 32; i++) {
+        const float *t = xyz + i * 9;
+        const rg_vec3 v0 = rg_v3(t[0], t[1], t[2]), v1 = rg_v3(t[3], t[4], t[5]), v2 = rg_v3(t[6], t[7], t[8]);
+        const rg_vec3 e0 = rg_sub(v2, v0), e1 = rg_sub(v1, v0), ab12 = rg_sub(v2, v1);
+        const float dot00 = rg_dot(e0, e0), dot01 = rg_dot(e0, e1), dot11 = rg_dot(e1, e1);
+        const float inv_denom = 1.0f / (dot00 * dot11 - dot01 * dot01);
+        const float len12 = rg_dot(ab12, ab12);
+        tab[i * 6 + 0] = make_float4(v0.x, v0.y, v0.z, dot00);
+        tab[i * 6 + 1] = make_float4(v1.x, v1.y, v1.z, dot01);
+        tab[i * 6 + 2] = make_float4(v2.x, v2.y, v2.z, dot11);
+        tab[i * 6 + 3] = make_float4(e0.x, e0.y, e0.z, inv_denom);
+        tab[i * 6 + 4] = make_float4(e1.x, e1.y, e1.z, len12);
+        tab[i * 6 + 5] = make_float4(ab12.x, ab12.y, ab12.z, 0.0f);
+    }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(ctx->d_cornell, tab, sizeof tab, cudaMemcpyHostToDevice));
+    ctx->have_cornell = true;
+    return RMDF_OK;
+}
+
+// ---- frame rendering ------------------------------------------------------------------
+struct WorkList {
+    bool full_frame;
+    unsigned long long mask;
+    int n_tiles, tile_w, tile_h;
+    int64_t out_pixels;
+    int out_stride;
+};
+
+static int build_worklist(const rmdf_params *p, WorkList *wl)
+{
+    if (!p) return fail(RMDF_ERR_ARG, "params is NULL");
+    if (p->scene < 0 || p->scene > 3) return fail(RMDF_ERR_ARG, "scene %d out of range [0,3]", p->scene);
+    if (p->fb_w < 1 || p->fb_h < 1 || p->fb_w > 131072 || p->fb_h > 131072) return fail(RMDF_ERR_ARG, "frame buffer %dx%d out of range", p->fb_w, p->fb_h);
+    if (p->resolve_log2 < 0 || p->resolve_log2 > 3) return fail(RMDF_ERR_ARG, "resolve_log2 %d out of range [0,3]", p->resolve_log2);
+    if (p->out_format != RMDF_OUT_RGBA8 && p->out_format != RMDF_OUT_RGBA32F) return fail(RMDF_ERR_ARG, "out_format %d unknown", p->out_format);
+    if (p->out_format == RMDF_OUT_RGBA32F && p->resolve_log2 != 0) return fail(RMDF_ERR_ARG, "RGBA32F output requires resolve_log2 = 0");
+    if (p->mode != RMDF_MODE_PARITY && p->mode != RMDF_MODE_FAST) return fail(RMDF_ERR_ARG, "mode %d unknown", p->mode);
+    if (p->lod_policy != RMDF_LOD_QUAD && p->lod_policy != RMDF_LOD_ALWAYS_LINEAR) return fail(RMDF_ERR_ARG, "lod_policy %d unknown", p->lod_policy);
+    if (p->layout != RMDF_LAYOUT_FRAME && p->layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", p->layout);
+    for (int i = 0; i < 4; i++) if (p->reserved[i]) return fail(RMDF_ERR_ARG, "reserved fields must be 0");
+    const int k = p->resolve_log2, q = 1 << k;
+    const bool sharded = p->shard_count > 1;
+    if (sharded && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", p->shard_rank, p->shard_count);
+    if (p->shard_count > 64) return fail(RMDF_ERR_ARG, "shard_count %d > 64 tiles", p->shard_count);
+    wl->full_frame = (p->tile_idx < 0) && !sharded;
+    if (wl->full_frame) {
+        if ((p->fb_w % q) || (p->fb_h % q)) return fail(RMDF_ERR_ARG, "frame %dx%d is not a multiple of the %dx%d resolve footprint", p->fb_w, p->fb_h, q, q);
+        if (p->layout != RMDF_LAYOUT_FRAME) return fail(RMDF_ERR_ARG, "packed layout needs tile_idx >= 0 or shard_count > 1");
+        wl->mask = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
+        wl->out_stride = p->fb_w >> k;
+        wl->out_pixels = (int64_t)(p->fb_w >> k) * (p->fb_h >> k);
+        return RMDF_OK;
+    }
+    // 8×8 tile grid, ShaderRendering.hs:49-52,183-193.  Tile edges must fall on even
+    // pixel boundaries so that no 2×2 fragment quad straddles two tiles.
+    if ((p->fb_w % 16) || (p->fb_h % 16)) return fail(RMDF_ERR_UNSUPPORTED, "tiled rendering needs frame dimensions divisible by 16 (got %dx%d)", p->fb_w, p->fb_h);
+    wl->tile_w = p->fb_w / 8; wl->tile_h = p->fb_h / 8;
+    if ((wl->tile_w % q) || (wl->tile_h % q)) return fail(RMDF_ERR_ARG, "tile %dx%d is not a multiple of the %dx%d resolve footprint", wl->tile_w, wl->tile_h, q, q);
+    unsigned long long mask = 0;
+    for (int t = 0; t < 64; t++) {
+        const int tx = t & 7, ty = t >> 3;
+        bool sel = true;
+        if (p->tile_idx >= 0) sel = sel && (t == (p->tile_idx % 64));
+        if (sharded) sel = sel && (((tx + ty) % p->shard_count) == p->shard_rank);
+        if (sel) mask |= 1ull << t;
+    }
+    wl->mask = mask;
+    wl->n_tiles = __builtin_popcountll(mask);
+    if (p->layout == RMDF_LAYOUT_PACKED_TILES) {
+        wl->out_stride = wl->tile_w >> k;
+        wl->out_pixels = (int64_t)wl->n_tiles * (wl->tile_w >> k) * (wl->tile_h >> k);
+    } else {
+        wl->out_stride = p->fb_w >> k;
+        wl->out_pixels = (int64_t)(p->fb_w >> k) * (p->fb_h >> k);
+    }
+    return RMDF_OK;
+}
+
+extern "C" int64_t rmdf_render_output_pixels(const rmdf_params *p, int32_t *n_tiles)
+{
+    WorkList wl;
+    if (build_worklist(p, &wl)) return -1;
+    if (n_tiles) *n_tiles = wl.n_tiles;
+    return wl.out_pixels;
+}
+
+// orbit camera + lookat (fragment.shd:829-838, 884-902), hoisted: it is constant per frame
+static void make_camera(int scene, float in_time, float cam[12])
+{
+    rg_vec3 cam_pos;
+    if (scene == RMDF_SCENE_CORNELL_BOX) {
+        cam_pos.x = rg_sin(in_time / 2.0f) * 0.4f;
+        cam_pos.z = -2.0f;
+        cam_pos.y = rg_cos(in_time / 2.0f) * 0.4f;
+    } else {
+        cam_pos.x = rg_sin(in_time / 3.0f);
+        cam_pos.z = rg_cos(in_time / 3.0f);
+        cam_pos.y = rg_cos(in_time / 4.0f);
+        cam_pos = rg_scale(rg_normalize(cam_pos), 2.414213562373095f);
+    }
+    const rg_vec3 zaxis = rg_normalize(rg_sub(cam_pos, rg_v3(0.0f, 0.0f, 0.0f)));
+    const rg_vec3 xaxis = rg_normalize(rg_cross(rg_v3(0.0f, 1.0f, 0.0f), zaxis));
+    const rg_vec3 yaxis = rg_cross(zaxis, xaxis);
+    cam[0] = xaxis.x; cam[1] = xaxis.y; cam[2] = xaxis.z;
+    cam[3] = yaxis.x; cam[4] = yaxis.y; cam[5] = yaxis.z;
+    cam[6] = zaxis.x; cam[7] = zaxis.y; cam[8] = zaxis.z;
+    cam[9] = cam_pos.x; cam[10] = cam_pos.y; cam[11] = cam_pos.z;
+}
+
+static int pick_item_h(int64_t blocks_of_32_rows, int resident_warps, int k)
+{
+    // shrink the work item until there are ≥ 4 items per resident warp (small frames)
+    int item_h = 32;
+    const int min_h = (1 << k) > 4 ? (1 << k) : 4;
+    while (item_h > min_h && blocks_of_32_rows * (32 / item_h) < (int64_t)resident_warps * 4) item_h >>= 1;
+    return item_h;
+}
+
+extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    WorkList wl;
+    if ((rc = build_worklist(p, &wl))) return rc;
+    if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    if (p->scene == RMDF_SCENE_CORNELL_BOX && !ctx->have_cornell)
+        return fail(RMDF_ERR_STATE, "Cornell scene requested before rmdf_set_cornell");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+
+    MarchParams mp;
+    memset(&mp, 0, sizeof mp);
+    mp.scene = p->scene; mp.fb_w = p->fb_w; mp.fb_h = p->fb_h;
+    mp.fw = (float)p->fb_w; mp.fh = (float)p->fb_h;
+    mp.aspect = mp.fw / mp.fh;
+    mp.fov_xs = rg_tan(rg_radians(45.0f * 1.5f) / 2.0f);               // fragment.shd:866-867,910
+    make_camera(p->scene, p->time, mp.cam);
+    {                                                                   // fragment.shd:116-119
+        float pow_offs = rg_mod(p->time / 2.0f, 9.0f);
+        if (pow_offs > 4.5f) pow_offs = 9.0f - pow_offs;
+        mp.power = pow_offs + 2.0f;
+    }
+    mp.bsphere_r = (p->scene == RMDF_SCENE_MB_POWER8) ? 1.15f : (p->scene == RMDF_SCENE_MB_GENERAL) ? 1.5f : 1.0f;
+    mp.lod_policy = p->lod_policy; mp.resolve_log2 = p->resolve_log2;
+    mp.out_format = p->out_format; mp.layout = p->layout;
+    mp.full_frame = wl.full_frame ? 1 : 0;
+    mp.tile_mask = wl.mask; mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
+    mp.out_stride = wl.out_stride;
+    for (int s = 0; s < RMDF_ENV_SLOTS; s++) {
+        mp.env_point[s] = ctx->env[s].tex_point;
+        mp.env_cube[s] = ctx->env[s].tex_cube;
+        mp.env_face[s] = ctx->env[s].face_w;
+    }
+    mp.cornell = ctx->d_cornell;
+    mp.out = fb_dev;
+    mp.queue = ctx->d_queue;
+    mp.counters = ctx->d_counters;
+
+    const int ctas_per_sm = (p->mode == RMDF_MODE_FAST) ? march_fast_ctas_per_sm(p->scene) : march_parity_ctas_per_sm(p->scene);
+    const int resident_warps = ctas_per_sm * ctx->sm_count * kWarpsPerCta;
+    const int bx = (wl.tile_w + kBlockDim - 1) / kBlockDim;
+    const int64_t blocks32 = (int64_t)bx * ((wl.tile_h + 31) / 32) * wl.n_tiles;
+    mp.item_h = pick_item_h(blocks32, resident_warps, p->resolve_log2);
+    mp.blocks_x = bx;
+    mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
+    const int64_t n_items = (int64_t)mp.blocks_x * mp.blocks_y * wl.n_tiles;
+    if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
+    mp.n_items = (int)n_items;
+    if (mp.n_items == 0) return RMDF_OK;
+    int grid = ctas_per_sm * ctx->sm_count;
+    const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+
+    CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = (p->mode == RMDF_MODE_FAST) ? launch_march_fast(mp, grid, ctx->stream)
+                                                : launch_march_parity(mp, grid, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "march kernel launch: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->launches++;
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
+{
+    int rc = use(ctx); if (rc) return rc;
+    WorkList wl;
+    if ((rc = build_worklist(p, &wl))) return rc;
+    if (!fb_host) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    const size_t px_bytes = (p->out_format == RMDF_OUT_RGBA32F) ? 16 : 4;
+    const size_t bytes = (size_t)wl.out_pixels * px_bytes;
+    if ((rc = ensure_staging(ctx, bytes))) return rc;
+    const bool partial = !wl.full_frame && p->layout == RMDF_LAYOUT_FRAME;
+    if (partial)   // drawShaderTile leaves the rest of the FBO untouched: start from the caller's pixels
+        CU(cudaMemcpyAsync(ctx->d_out, fb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = rmdf_render_device(ctx, p, ctx->d_out))) return rc;
+    CU(cudaMemcpyAsync(fb_host, ctx->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RMDF_OK;
+}
+
+// ---- Julia ---------------------------------------------------------------------------------
+static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int y0, int y1, int k, JuliaParams *jp)
+{
+    if (w < 1 || h < 1 || w > 131072 || h > 131072) return fail(RMDF_ERR_ARG, "julia frame %dx%d out of range", w, h);
+    if (k < 0 || k > 3) return fail(RMDF_ERR_ARG, "resolve_log2 %d out of range [0,3]", k);
+    const int q = 1 << k;
+    if (y0 < 0 || y1 > h || y0 >= y1) return fail(RMDF_ERR_ARG, "julia rows [%d,%d) outside [0,%d)", y0, y1, h);
+    if ((w % q) || (y0 % q) || (y1 % q)) return fail(RMDF_ERR_ARG, "julia width/rows must be multiples of %d", q);
+    memset(jp, 0, sizeof *jp);
+    // Fractal2D.hs:65-76 (host, libm like GHC's Float primops)
+    const float pi = 3.14159265358979323846f;
+    const float f_tick = (float)tick;
+    const float q1 = f_tick / 17.0f, q2 = f_tick / 61.0f, q3 = f_tick / 71.0f;
+    const float st1 = q1 - truncf(q1), st2 = q2 - truncf(q2), st3 = q3 - truncf(q3);
+    const float two_pi = st1 * 2.0f * pi;
+    jp->julia_r = sinf(two_pi) * (0.7f > st2 ? 0.7f : st2);
+    jp->julia_i = cosf(two_pi) * (0.7f > st3 ? 0.7f : st3);
+    jp->w = w; jp->h = h; jp->y0 = y0; jp->y1 = y1; jp->smooth = smooth ? 1 : 0; jp->resolve_log2 = k;
+    jp->fw = (float)w; jp->fh = (float)h;
+    jp->ratio = jp->fw / jp->fh;
+    jp->xshift = 1.45f * jp->ratio;
+    const int ctas = julia_ctas_per_sm();
+    const int resident_warps = ctas * ctx->sm_count * kWarpsPerCta;
+    const int bx = (w + kBlockDim - 1) / kBlockDim;
+    jp->item_h = pick_item_h((int64_t)bx * ((y1 - y0 + 31) / 32), resident_warps, k);
+    jp->blocks_x = bx;
+    jp->blocks_y = (y1 - y0 + jp->item_h - 1) / jp->item_h;
+    const int64_t n = (int64_t)jp->blocks_x * jp->blocks_y;
+    if (n > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "julia frame too large");
+    jp->n_items = (int)n;
+    jp->out_stride = w >> k;
+    jp->queue = ctx->d_queue;
+    jp->counters = ctx->d_counters;
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
+                                 int y0, int y1, int resolve_log2, void *fb_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    JuliaParams jp;
+    if ((rc = julia_params(ctx, w, h, smooth, tick, y0, y1, resolve_log2, &jp))) return rc;
+    jp.out = (uint32_t *)fb_dev;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    int grid = julia_ctas_per_sm() * ctx->sm_count;
+    const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+    CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = launch_julia(jp, grid, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "julia kernel launch: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->ev_valid = true;
+    ctx->launches++;
+    return RMDF_OK;
+}
+
+extern "C" int rmdf_julia(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
+                          int y0, int y1, int resolve_log2, uint32_t *fb_host)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!fb_host) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    if (resolve_log2 < 0 || resolve_log2 > 3 || y1 <= y0 || w < 1) return fail(RMDF_ERR_ARG, "rmdf_julia: bad arguments");
+    const size_t bytes = sizeof(uint32_t) * (size_t)(w >> resolve_log2) * (size_t)((y1 - y0) >> resolve_log2);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if ((rc = ensure_staging(ctx, bytes))) return rc;
+    if ((rc = rmdf_julia_device(ctx, w, h, smooth, tick, y0, y1, resolve_log2, ctx->d_out))) return rc;
+    CU(cudaMemcpyAsync(fb_host, ctx->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RMDF_OK;
+}
+
+// ---- frame-buffer helpers ----------------------------------------------------------------
+extern "C" int rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w, int h, int levels, void *out_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!fb_dev || !out_dev || w < 1 || h < 1 || levels < 0 || levels > 16 || (w >> levels) < 1 || (h >> levels) < 1)
+        return fail(RMDF_ERR_ARG, "rmdf_mip_resolve_device: bad arguments");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaError_t e = launch_mip_resolve((const uint32_t *)fb_dev, w, h, levels, (uint32_t *)out_dev, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "mip resolve: %s", cudaGetErrorString(e));
+    ctx->launches += (uint64_t)(levels > 0 ? levels : 0);
+    return RMDF_OK;
+}
+
+// ---- counters -----------------------------------------------------------------------------
+extern "C" int rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!out) return fail(RMDF_ERR_ARG, "out is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    unsigned long long h[C_NSLOTS];
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->samples = h[C_SAMPLES]; out->in_sphere = h[C_IN_SPHERE]; out->hits = h[C_HITS];
+    out->march_de = h[C_MARCH_DE]; out->shade_de = h[C_SHADE_DE]; out->inner_iters = h[C_ITERS];
+    out->launches = ctx->launches;
+    if (ctx->ev_valid) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) out->last_kernel_ms = ms;
+    }
+    return RMDF_OK;
+}
+extern "C" int rmdf_counters_reset(rmdf_ctx *ctx)
+{
+    int rc = use(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS, ctx->stream));
+    return RMDF_OK;
+}

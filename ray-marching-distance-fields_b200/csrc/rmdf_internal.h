@@ -1,0 +1,66 @@
+// rmdf_internal.h — types shared by the C-ABI layer (rmdf_api.cu) and the kernel
+// translation units.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rmdf {
+
+constexpr int kBlockDim     = 32;    // a work item is a 32×32 block of frame-buffer samples
+constexpr int kWarpsPerCta  = 8;
+constexpr int kCtaThreads   = kWarpsPerCta * 32;
+constexpr int kCornellF4    = 32 * 6; // 32 triangles × 6 float4 of precomputed terms
+
+enum CounterSlot { C_SAMPLES = 0, C_IN_SPHERE, C_HITS, C_MARCH_DE, C_SHADE_DE, C_ITERS, C_NSLOTS = 8 };
+
+// Everything one frame needs, passed by value as the kernel parameter.
+struct MarchParams {
+    int   scene, fb_w, fb_h;
+    float fw, fh, aspect, fov_xs;     // in_screen_wdh/hgt as float, w/h, tan(hfov/2)
+    float cam[12];                    // x̂, ŷ, ẑ, eye  (lookat, fragment.shd:829-838)
+    float power;                      // animated Mandelbulb power (fragment.shd:116-119)
+    float bsphere_r;                  // fragment.shd:640-649
+    int   lod_policy, resolve_log2, out_format, layout;
+    // work list: either the whole frame or a subset of the reference's 8×8 tile grid
+    int   full_frame;
+    unsigned long long tile_mask;
+    int   tile_w, tile_h;             // level-0 size of one tile
+    int   item_h;                     // rows per work item: 4, 8, 16 or 32
+    int   blocks_x, blocks_y;         // 32×item_h blocks per rect
+    int   n_items;
+    int   out_stride;                 // output row stride in pixels (already >> resolve_log2)
+    // resources
+    cudaTextureObject_t env_point[5]; // layered 2D half4, point sampled (parity path)
+    cudaTextureObject_t env_cube[5];  // cube map half4, linear + seamless (fast path)
+    int   env_face[5];                // face width, 0 = unbound (samples as constant 1.0)
+    const float4 *cornell;            // kCornellF4 float4 (precomputed triangle terms)
+    void *out;
+    unsigned int *queue;              // work-queue counter (zeroed before the launch)
+    unsigned long long *counters;     // C_NSLOTS totals
+};
+
+struct JuliaParams {
+    int   w, h, y0, y1, smooth, resolve_log2;
+    float julia_r, julia_i, fw, fh, ratio, xshift;
+    int   item_h, blocks_x, blocks_y, n_items;
+    int   out_stride;
+    uint32_t *out;
+    unsigned int *queue;
+    unsigned long long *counters;
+};
+
+// launchers implemented in march_parity.cu / march_fast.cu / julia.cu / envmap.cu
+cudaError_t launch_march_parity(const MarchParams &p, int grid, cudaStream_t s);
+cudaError_t launch_march_fast(const MarchParams &p, int grid, cudaStream_t s);
+int         march_parity_ctas_per_sm(int scene);
+int         march_fast_ctas_per_sm(int scene);
+cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s);
+int         julia_ctas_per_sm();
+cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_dev, int np,
+                            float *out_dev, cudaStream_t s);
+cudaError_t launch_resize(const float *src_dev, int w, int h, int dstw, int dsth, float *out_dev, cudaStream_t s);
+cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int face_w, float *faces_dev, cudaStream_t s);
+cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s);
+cudaError_t launch_mip_resolve(const uint32_t *in_dev, int w, int h, int levels, uint32_t *out_dev, cudaStream_t s);
+
+}  // namespace rmdf
