@@ -176,6 +176,10 @@ typedef struct {
 int  rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out);
 int  rmdf_counters_reset(rmdf_ctx *ctx);
 
+/* FP32 FMA roofline denominator: an FFMA-chain microbenchmark on ctx's device (the
+ * reference has no counterpart).  tflops = 2·FFMA/s, sm_mhz = SM clock sustained. */
+int  rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,10 +4,11 @@ when there is no sm_100 GPU."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "librmdf_b200.so"
+LIB_PATH = Path(os.environ["RMDF_LIB"]) if os.environ.get("RMDF_LIB") else HERE / "librmdf_b200.so"   # RMDF_LIB: tuning variants
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = range(5)
 SCENE_CORNELL_BOX, SCENE_DE_TEST, SCENE_MB_POWER8, SCENE_MB_GENERAL = range(4)
@@ -22,7 +23,7 @@ EXPORTS = [
     "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device",
     "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
-    "rmdf_julia", "rmdf_julia_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset",
+    "rmdf_julia", "rmdf_julia_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak",
 ]
 
 
@@ -93,6 +94,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_mip_resolve_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.rmdf_counters_reset.argtypes = [vp]
+    L.rmdf_measure_fp32_peak.argtypes = [vp, fp, fp]
     for name in EXPORTS:
         f = getattr(L, name)
         if name not in ("rmdf_destroy", "rmdf_last_error", "rmdf_render_output_pixels"):

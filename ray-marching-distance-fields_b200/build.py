@@ -28,6 +28,7 @@ UNITS = {
     "march_fast.cu": ["--use_fast_math"],
     "envmap.cu": ["-fmad=false"],
     "julia.cu": ["-fmad=false"],
+    "peak.cu": [],
 }
 
 
@@ -42,8 +43,12 @@ def _deps():
     return list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((HERE.parent / "include").glob("*.h"))
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, extra=(), out: Path = LIB, objdir: Path = OBJ) -> Path:
+    """extra: additional nvcc flags (e.g. -DRMDF_MIN_CTAS=3) for tuning variants; out/objdir
+    let a variant live beside the default library (RMDF_LIB selects it at load time)."""
+    global OBJ, LIB
     nvcc = _nvcc()
+    OBJ, LIB = Path(objdir), Path(out)
     OBJ.mkdir(exist_ok=True)
     newest_dep = max(p.stat().st_mtime for p in _deps() + [Path(__file__)])
     objs, rebuilt = [], False
@@ -52,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs.append(str(obj))
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_dep):
             continue
-        cmd = [nvcc] + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(src), "-o", str(obj)]
+        cmd = [nvcc] + COMMON + flags + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout)
@@ -68,4 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", default="", help="name of a tuning variant: builds librmdf_b200_<name>.so")
+    ap.add_argument("--extra", default="", help="extra nvcc flags, space separated")
+    a = ap.parse_args()
+    if a.variant:
+        print(build(True, a.verbose, a.extra.split(), HERE / ("librmdf_b200_%s.so" % a.variant), HERE / ("build_" + a.variant)))
+    else:
+        print(build(a.force, a.verbose, a.extra.split()))

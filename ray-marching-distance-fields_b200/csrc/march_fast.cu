@@ -9,7 +9,14 @@ namespace rmdf {
 
 struct MathFast {
     static constexpr bool kFast = true;
-    static constexpr int  kMinCtas = 2;
+#ifndef RMDF_FAST_MIN_CTAS
+#define RMDF_FAST_MIN_CTAS 2
+#endif
+#ifndef RMDF_FAST_DE_NOINLINE
+#define RMDF_FAST_DE_NOINLINE 0
+#endif
+    static constexpr int  kMinCtas = RMDF_FAST_MIN_CTAS;
+    static constexpr bool kNoinlineDE = RMDF_FAST_DE_NOINLINE;
     static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float inversesqrt(float x) { return rsqrtf(x); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }

@@ -692,6 +692,18 @@ extern "C" int rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w,
     return RMDF_OK;
 }
 
+// ---- measurement ----------------------------------------------------------------------------
+extern "C" int rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!tflops || !sm_mhz) return fail(RMDF_ERR_ARG, "rmdf_measure_fp32_peak: NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaError_t e = measure_fp32_peak(ctx->sm_count, ctx->stream, tflops, sm_mhz);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_measure_fp32_peak: %s", cudaGetErrorString(e));
+    ctx->launches += 6;
+    return RMDF_OK;
+}
+
 // ---- counters -----------------------------------------------------------------------------
 extern "C" int rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out)
 {

@@ -372,6 +372,11 @@ class ShaderRenderer:
         check(self._lib.rmdf_counters_get(self._h, C.byref(c)))
         return c.as_dict()
 
+    def measureFp32Peak(self) -> dict:
+        t, f = C.c_float(0), C.c_float(0)
+        check(self._lib.rmdf_measure_fp32_peak(self._h, C.byref(t), C.byref(f)))
+        return {"tflops": float(t.value), "sm_mhz": float(f.value)}
+
     def resetCounters(self) -> None:
         check(self._lib.rmdf_counters_reset(self._h))
 
