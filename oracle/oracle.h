@@ -36,6 +36,7 @@ int   oracle_render(const oracle_frame *f, int x0, int y0, int x1, int y1,
 void  oracle_camera(int scene, float in_time, float cam[12]);
 float oracle_mb_power(float in_time);
 float oracle_distance(int scene, float in_time, const float *cornell, float x, float y, float z);
+void  oracle_glsl_eval(int fn, const float *x, const float *y, float *out, int64_t n);
 
 /* HDREnvMap.hs / CoordTransf.hs / CornellBox.hs (oracle_envmap.c) */
 int  oracle_hdr_decode(const uint8_t *file, int64_t nbytes, int *w, int *h, float *rgb, int64_t cap_floats);

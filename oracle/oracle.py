@@ -67,6 +67,7 @@ def lib():
         L.oracle_mb_power.argtypes = [C.c_float]; L.oracle_mb_power.restype = C.c_float
         L.oracle_distance.argtypes = [C.c_int, C.c_float, fp, C.c_float, C.c_float, C.c_float]
         L.oracle_distance.restype = C.c_float
+        L.oracle_glsl_eval.argtypes = [C.c_int, fp, fp, fp, C.c_int64]
         L.oracle_hdr_decode.argtypes = [u8p, C.c_int64, ip, ip, fp, C.c_int64]; L.oracle_hdr_decode.restype = C.c_int
         L.oracle_hdr_encode.argtypes = [fp, C.c_int, C.c_int, u8p, C.c_int64]; L.oracle_hdr_encode.restype = C.c_int64
         L.oracle_rgbe_roundtrip.argtypes = [fp, C.c_int64, fp]
@@ -149,6 +150,19 @@ def render(scene: int, fb_w: int, fb_h: int, time: float = 0.0, envs=None, rect=
     if rc != 0:
         raise ValueError("oracle_render failed with code %d" % rc)
     return {"fb": fb, "linear": lin, "hit": hit, "counters": cnt.as_dict()}
+
+
+GLSL_FN = {"log": 0, "exp": 1, "pow": 2, "sin": 3, "cos": 4, "tan": 5, "acos": 6, "atan2": 7,
+           "inversesqrt": 8, "round_to_half": 9, "unorm8": 10, "mod": 11}
+
+
+def glsl(fn: str, x, y=None) -> np.ndarray:
+    """Element-wise include/rmdf_glsl.h built-in `fn` (float32 in, float32 out)."""
+    x = _f32(x).ravel()
+    y = _f32(np.zeros_like(x) if y is None else np.broadcast_to(y, x.shape)).ravel()
+    out = np.empty_like(x)
+    lib().oracle_glsl_eval(GLSL_FN[fn], _fp(x), _fp(y), _fp(out), x.size)
+    return out
 
 
 # ---------------------------------------------------------------- env maps

@@ -41,6 +41,7 @@ struct EnvSlot {
     cudaArray_t arr_layered = nullptr, arr_cube = nullptr;
     cudaTextureObject_t tex_point = 0, tex_cube = 0;
     float *faces_dev = nullptr;        // 6·w·w·3 half-rounded floats (for rmdf_envmap_get_cube)
+    void *half4_dev = nullptr;         // 6·w·w half4 staging for the array copies
 };
 
 struct rmdf_ctx {
@@ -120,6 +121,7 @@ static void free_slot(EnvSlot &s)
     if (s.arr_layered) cudaFreeArray(s.arr_layered);
     if (s.arr_cube) cudaFreeArray(s.arr_cube);
     if (s.faces_dev) cudaFree(s.faces_dev);
+    if (s.half4_dev) cudaFree(s.half4_dev);
     s = EnvSlot();
 }
 
@@ -247,29 +249,31 @@ extern "C" int rmdf_rgbe_roundtrip(float *rgb, int64_t npix)
     return RMDF_OK;
 }
 
+// (re)fill a slot's two arrays from s.faces_dev; creates arrays + texture objects on first use
+// and re-uses them when the face width is unchanged (per-frame uploads stay allocation-free)
 static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *faces_dev_src)
 {
-    // faces_dev_src: 6·fw·fw·3 floats already on the device (ownership moves to the slot)
     cudaStream_t st = ctx->stream;
     const size_t ntex = (size_t)6 * fw * fw;
-    void *d_half4 = nullptr;
-    CU(cudaMalloc(&d_half4, ntex * 8));
-    cudaError_t e = launch_pack_half4(faces_dev_src, fw, d_half4, st);
+    const bool fresh = (s.arr_layered == nullptr);
+    cudaError_t e = cudaSuccess;
+    if (!s.half4_dev) e = cudaMalloc(&s.half4_dev, ntex * 8);
+    if (e == cudaSuccess) e = launch_pack_half4(faces_dev_src, fw, s.half4_dev, st);
     ctx->launches++;
     const cudaChannelFormatDesc desc = cudaCreateChannelDescHalf4();
     const cudaExtent ext = make_cudaExtent((size_t)fw, (size_t)fw, 6);
-    if (e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_layered, &desc, ext, cudaArrayLayered);
-    if (e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_cube, &desc, ext, cudaArrayCubemap);
+    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_layered, &desc, ext, cudaArrayLayered);
+    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_cube, &desc, ext, cudaArrayCubemap);
     for (int which = 0; which < 2 && e == cudaSuccess; which++) {
         cudaMemcpy3DParms cp;
         memset(&cp, 0, sizeof cp);
-        cp.srcPtr = make_cudaPitchedPtr(d_half4, (size_t)fw * 8, (size_t)fw, (size_t)fw);
+        cp.srcPtr = make_cudaPitchedPtr(s.half4_dev, (size_t)fw * 8, (size_t)fw, (size_t)fw);
         cp.dstArray = which ? s.arr_cube : s.arr_layered;
         cp.extent = ext;
         cp.kind = cudaMemcpyDeviceToDevice;
         e = cudaMemcpy3DAsync(&cp, st);
     }
-    if (e == cudaSuccess) {
+    if (fresh && e == cudaSuccess) {
         cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
         rd.resType = cudaResourceTypeArray;
         cudaTextureDesc td; memset(&td, 0, sizeof td);
@@ -286,8 +290,6 @@ static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *fa
             e = cudaCreateTextureObject(&s.tex_cube, &rd, &td, nullptr);
         }
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_half4);
     if (e != cudaSuccess) {
         free_slot(s);
         return fail(RMDF_ERR_CUDA, "env-map texture setup: %s", cudaGetErrorString(e));
@@ -302,14 +304,20 @@ extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     if (!faces_rgb || face_w < 1 || face_w > 8192) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind_cube: bad faces (w = %d)", face_w);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    CU(cudaStreamSynchronize(ctx->stream));
-    free_slot(ctx->env[slot]);
     EnvSlot &s = ctx->env[slot];
     const size_t bytes = sizeof(float) * 3 * 6 * (size_t)face_w * face_w;
-    CU(cudaMalloc(&s.faces_dev, bytes));
+    if (s.face_w != face_w) {                       // first bind or a size change: reallocate
+        CU(cudaStreamSynchronize(ctx->stream));
+        free_slot(s);
+        CU(cudaMalloc(&s.faces_dev, bytes));
+    }
+    // stream-ordered: a render already queued on the stream keeps sampling the old texels
     cudaError_t e = cudaMemcpyAsync(s.faces_dev, faces_rgb, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { free_slot(s); return fail(RMDF_ERR_CUDA, "rmdf_envmap_bind_cube: %s", cudaGetErrorString(e)); }
-    return make_slot_textures(ctx, s, face_w, s.faces_dev);
+    rc = make_slot_textures(ctx, s, face_w, s.faces_dev);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));         // the caller's buffer is not referenced after return
+    return RMDF_OK;
 }
 
 extern "C" int rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rgb, int w, int h)
@@ -332,7 +340,10 @@ extern "C" int rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rg
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_ll);
     if (e != cudaSuccess) { free_slot(s); return fail(RMDF_ERR_CUDA, "rmdf_envmap_bind: %s", cudaGetErrorString(e)); }
-    return make_slot_textures(ctx, s, fw, s.faces_dev);
+    rc = make_slot_textures(ctx, s, fw, s.faces_dev);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RMDF_OK;
 }
 
 extern "C" int rmdf_envmap_get_cube(rmdf_ctx *ctx, int slot, float *faces_rgb, int *face_w)

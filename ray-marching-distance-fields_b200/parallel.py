@@ -38,3 +38,18 @@ def assemble_tiles_torch(gathered, w: int, h: int, count: int):
     perm = torch.as_tensor(tile_permutation(count), device=gathered.device)
     tiles = gathered.reshape(64, th, tw).index_select(0, perm)
     return tiles.reshape(8, 8, th, tw).permute(0, 2, 1, 3).reshape(h, w)
+
+
+def gather_frame(packed, w: int, h: int, world: int, rank: int, gather_list=None):
+    """Rank-local packed tiles (1-D int32 tensor, CUDA+NCCL or CPU+gloo) → the [h, w] frame on
+    rank 0 (None elsewhere).  One gather, no other collective."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return packed.reshape(h, w)
+    if rank == 0 and gather_list is None:
+        gather_list = [torch.empty_like(packed) for _ in range(world)]
+    dist.gather(packed, gather_list if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    return assemble_tiles_torch(torch.stack(gather_list), w, h, world)

@@ -1,0 +1,193 @@
+"""Host-side logic and the C-ABI surface, without a GPU: the shared library loads and exports
+every symbol include/rmdf.h declares, argument validation and sizing are pure host code,
+compute entry points fail loudly without a device, and the multi-rank gather/assemble path
+runs under gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(R):
+    L = R._capi.load(build_if_missing=True)
+    hdr = (ROOT / "include" / "rmdf.h").read_text()
+    declared = sorted(set(re.findall(r"\b(rmdf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(L, name), "librmdf_b200.so does not export %s" % name
+    assert sorted(R._capi.EXPORTS) == declared
+    assert L.rmdf_abi_version() == 1
+    # no torch / python types in the signatures: the header is plain C
+    out = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", str(ROOT / "include" / "rmdf.h")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    out = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", str(ROOT / "include" / "rmdf_glsl.h")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure path")
+def test_no_cpu_fallback(R):
+    with pytest.raises(R.RmdfError) as e:
+        R.ShaderRenderer(0)
+    assert e.value.code == R._capi.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def _params(R, **kw):
+    p = R.Params()
+    p.scene, p.fb_w, p.fb_h, p.tile_idx, p.shard_count = 2, 256, 128, -1, 1
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def test_output_sizing_and_validation(R):
+    L = R._capi.load()
+    nt = C.c_int32()
+    n = lambda **kw: L.rmdf_render_output_pixels(C.byref(_params(R, **kw)), C.byref(nt))
+    assert n() == 256 * 128 and nt.value == 1
+    assert n(resolve_log2=2) == 64 * 32
+    assert n(tile_idx=5) == 256 * 128 and nt.value == 1                     # frame layout: untouched pixels stay
+    assert n(tile_idx=5, layout=R.LAYOUT_PACKED_TILES) == 32 * 16
+    assert n(tile_idx=69, layout=R.LAYOUT_PACKED_TILES) == 32 * 16          # idx mod 64
+    for g in (2, 4, 8):
+        assert n(shard_count=g, shard_rank=g - 1, layout=R.LAYOUT_PACKED_TILES, resolve_log2=1) == (64 // g) * 16 * 8
+        assert nt.value == 64 // g
+    # errors: every one sets rmdf_last_error
+    for bad in (dict(scene=4), dict(fb_w=0), dict(resolve_log2=4), dict(out_format=2), dict(mode=7), dict(lod_policy=3),
+                dict(out_format=R.OUT_RGBA32F, resolve_log2=1), dict(fb_w=250, resolve_log2=2), dict(fb_w=100, fb_h=100, tile_idx=0),
+                dict(shard_count=2, shard_rank=2), dict(layout=R.LAYOUT_PACKED_TILES), dict(shard_count=65, shard_rank=0)):
+        assert n(**bad) == -1, bad
+        assert len(L.rmdf_last_error()) > 0
+    p = _params(R); p.reserved[1] = 1
+    assert L.rmdf_render_output_pixels(C.byref(p), None) == -1
+    assert L.rmdf_render_output_pixels(None, None) == -1
+
+
+def test_host_only_entry_points_match_the_oracle(R, O, uffizi):
+    L = R._capi.load()
+    xyz = np.empty((96, 3), np.float32)
+    assert L.rmdf_cornell_box_vertices(xyz.ctypes.data) == 0
+    assert np.array_equal(xyz, O.cornell_vertices())
+    assert abs(np.abs(xyz).max() - 0.99 / np.sqrt(3)) < 1e-6                # fits the R = 1 bounding sphere
+    assert L.rmdf_cornell_box_vertices(None) != 0
+    img = (uffizi * np.float32(0.731)).copy()
+    mine = R.ShaderRenderer.rgbeRoundTrip(img)
+    assert np.array_equal(mine, O.rgbe_roundtrip(img))
+    assert L.rmdf_envmap_resize_height(512, 256, 256) == 128 == O.lib().oracle_resize_height(512, 256, 256)
+    assert L.rmdf_envmap_resize_height(500, 300, 7) == O.lib().oracle_resize_height(500, 300, 7)
+    assert L.rmdf_envmap_resize_height(0, 0, 0) == 0
+
+
+def test_hdr_file_io(R, O, uffizi, tmp_path):
+    raw = (ROOT / "data" / "uffizi_512.hdr").read_bytes()
+    assert np.array_equal(R.decodeHDR(raw), uffizi)
+    assert R.encodeHDR(uffizi) == O.hdr_encode(uffizi)
+    # new-style RLE scanlines decode to the same pixels (hand-encode two rows)
+    rgbe = np.frombuffer(R.encodeHDR(uffizi[:2, :16]), np.uint8)[-2 * 16 * 4:].reshape(2, 16, 4)
+    rle = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 16\n"
+    for y in range(2):
+        rle += bytes([2, 2, 0, 16])
+        for c in range(4):
+            rle += bytes([16]) + rgbe[y, :, c].tobytes()
+    assert np.array_equal(R.decodeHDR(rle), O.hdr_decode(rle))
+    assert np.array_equal(R.decodeHDR(rle), R.decodeHDR(R.encodeHDR(uffizi[:2, :16])))
+    with pytest.raises(ValueError):
+        R.loadHDRImage(tmp_path / "missing.hdr")
+    (tmp_path / "bad.hdr").write_bytes(b"P6\n1 1\n255\n\0\0\0")
+    with pytest.raises(ValueError):
+        R.loadHDRImage(tmp_path / "bad.hdr")
+    # cache-file naming of ShaderRendering.hs:72-75 (`show (8 :: Float)` = "8.0")
+    assert R.ShaderRenderer.mkCacheFn("./latlong_envmaps/uffizi_512.hdr", 8.0) == "./latlong_envmaps/uffizi_512_cache_pow_8.0.hdr"
+    assert R.ShaderRenderer.mkCacheFn("a/b.hdr", 512).endswith("b_cache_pow_512.0.hdr")
+
+
+def test_tile_enum_and_framebuffer(R, O, tmp_path):
+    assert [int(s) for s in R.FragmentShader] == [0, 1, 2, 3]
+    assert R.isTileIdxFirstTile(0) and R.isTileIdxFirstTile(128) and not R.isTileIdxFirstTile(1)
+    assert R.isTileIdxLastTile(63) and R.isTileIdxLastTile(127) and not R.isTileIdxLastTile(64)
+    fb = R.FrameBuffer(4, 2)
+    assert fb.getFrameBufferDim() == (4, 2) and (fb.data == 0xFF000000).all()
+    fb.fillFrameBuffer(lambda w, h, v: v.__setitem__(slice(None), np.arange(w * h, dtype=np.uint32) << 8))
+    fb.saveFrameBufferToPNG(tmp_path / "s.png")
+    from PIL import Image
+    img = np.array(Image.open(tmp_path / "s.png"))
+    assert np.array_equal(img, O.screenshot_rows(fb.data))                  # flipped rows, alpha 0xFF
+
+
+def test_tile_dealing_and_assembly(R):
+    from importlib import import_module
+    par = import_module("ray-marching-distance-fields_b200.parallel")
+    for g in (1, 2, 4, 8):
+        owned = [par.tiles_of_rank(r, g) for r in range(g)]
+        assert sorted(sum(owned, [])) == list(range(64)) and all(len(o) == 64 // g for o in owned)
+        # every rank holds tiles from every tile row and (g = 8) every column: balanced load
+        assert all(len({t >> 3 for t in o}) == 8 for o in owned)
+        w, h = 64, 32
+        frame = np.arange(w * h, dtype=np.uint32).reshape(h, w)
+        tiles = frame.reshape(8, h // 8, 8, w // 8).transpose(0, 2, 1, 3).reshape(64, h // 8, w // 8)
+        packed = [tiles[o].reshape(-1) for o in owned]
+        assert np.array_equal(par.assemble_tiles_numpy(packed, w, h, g), frame)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from importlib import import_module
+par = import_module("ray-marching-distance-fields_b200.parallel")
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=world)
+w, h = 128, 64
+frame = (np.arange(w * h, dtype=np.int64) * 2654435761 % (1 << 31)).astype(np.int32).reshape(h, w)
+tiles = frame.reshape(8, h // 8, 8, w // 8).transpose(0, 2, 1, 3).reshape(64, -1)
+mine = torch.from_numpy(np.ascontiguousarray(tiles[par.tiles_of_rank(rank, world)]).reshape(-1))
+out = par.gather_frame(mine, w, h, world, rank)
+if rank == 0:
+    assert out is not None and np.array_equal(out.numpy(), frame), "assembled frame differs"
+    print("GLOO_OK")
+else:
+    assert out is None
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_gather_frame_gloo_world_size_2(tmp_path):
+    """The N > 1 path of bench.py (tile sharding + one gather to rank 0) on CPU."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT), str(port)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "GLOO_OK" in outs[0]
+
+
+def test_bench_reference_arm_contract():
+    """--impl reference prints one JSON line with the contract's keys (tiny budget)."""
+    import json
+    env = dict(os.environ, RMDF_BENCH_CPU_BUDGET_S="0.5")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

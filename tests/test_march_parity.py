@@ -135,6 +135,22 @@ def test_fast_mode_within_tolerance(sr, O, R, oracle_envs):
     assert p >= 30.0        # 1 spp noise floor is ~40 dB; the 50 dB bar is for parity mode
 
 
+def test_fast_mode_16spp_meets_baseline_tolerance(sr, O, R, oracle_envs):
+    """BASELINE's bar at the headline sampling rate (16 spp = 4×4): hit masks >= 99.9 % equal and
+    linear-RGB PSNR >= 50 dB on the resolved image, fast build vs the oracle.  A 1024×576 frame
+    buffer = 256×144 output pixels keeps the oracle to a second."""
+    _bind(sr, oracle_envs)
+    w, h, s = 1024, 576, 4
+    ref = O.render(2, w, h, 0.0, envs=oracle_envs)
+    got = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, out_format=R.OUT_RGBA32F, mode=R.MODE_FAST)
+    agree = np.mean((got[..., 3] > 0.5) == ref["hit"].astype(bool))
+    box = lambda a: np.clip(np.nan_to_num(a), 0, 1).reshape(h // s, s, w // s, s, 3).mean(axis=(1, 3))
+    p = psnr(box(got[..., :3]), box(ref["linear"]))
+    print("fast mode 16 spp: hit agreement %.5f%%, linear PSNR %.2f dB" % (agree * 100, p))
+    assert agree >= 0.999
+    assert p >= 50.0
+
+
 def test_error_behaviour(sr, R):
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(5, None, 64, 64, 0.0)

@@ -1,0 +1,292 @@
+"""CPU tests of the oracle itself (no GPU): the committed golden vectors, an independent
+numpy/float32 re-derivation of the hot formulas straight from the reference text, the
+reference's own debug fixtures (buildTestLatLongEnvMap, HDREnvMap.hs:55-73) and the edge
+cases of its helpers (makeNSegments, ConcurrentSegments.hs:14-23).
+
+The reference ships no tests and cannot be executed here, so these pin the
+oracle to (a) its frozen known answers and (b) a second, independently written restatement."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+f32 = np.float32
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_golden_de_lattice(O):
+    g = json.loads((GOLD / "de_lattice.json").read_text())
+    pts = np.array(g["points"], np.uint32).view(np.float32)
+    for s in range(4):
+        got = O.distance(s, g["time"], pts).view(np.uint32)
+        assert np.array_equal(got, np.array(g["de_bits"][str(s)], np.uint32)), "scene %d" % s
+
+
+def _synthetic_envs(O):
+    rng = np.random.RandomState(1234)
+    envs = []
+    for w in (6, 4, 4, 3, 3):
+        e = rng.uniform(0.0, 2.0, size=(6, w, w, 3)).astype(np.float32)
+        envs.append(O.glsl("round_to_half", e).reshape(e.shape))
+    return envs
+
+
+def test_golden_frames(O):
+    z = np.load(GOLD / "frames_64.npz")
+    envs = _synthetic_envs(O)
+    for s in range(4):
+        for t in (0.0, 7.0):
+            assert np.array_equal(O.render(s, 64, 64, t)["fb"], z["white_s%d_t%d" % (s, int(t))])
+            assert np.array_equal(O.render(s, 64, 64, t, envs=envs)["fb"], z["env_s%d_t%d" % (s, int(t))])
+
+
+def test_golden_julia_camera_cornell(O):
+    z = np.load(GOLD / "julia_96x64.npz")
+    for t in (0.0, 7.0, 123.5):
+        for sm in (0, 1):
+            assert np.array_equal(O.julia(96, 64, bool(sm), t), z["j_t%d_s%d" % (int(t), sm)])
+    cams = json.loads((GOLD / "camera.json").read_text())
+    for key, bits in cams.items():
+        s, t = key.split("_")
+        assert np.array_equal(O.camera(int(s), float(t)).view(np.uint32), np.array(bits, np.uint32))
+    assert np.array_equal(O.cornell_vertices(), np.load(GOLD / "cornell_vertices.npy"))
+
+
+def test_golden_test_envmap_convolution(O):
+    z = np.load(GOLD / "test_envmap_conv.npz")
+    small = O.resize(O.test_latlong_envmap(), 32)
+    assert np.array_equal(small, z["small"])
+    assert np.array_equal(O.convolve(small, 1.0), z["p1"])
+    assert np.array_equal(O.convolve(small, 8.0, threads=1), z["p8"])       # thread count must not matter
+
+
+# ------------------------------------------------------------------ independent restatements
+def _np_mandelbulb8(O, p):
+    """fragment.shd:74-99,101-158 (POWER8) written again in numpy float32, vectorised."""
+    p = np.asarray(p, f32)
+    pos = np.stack([p[:, 2], p[:, 0], p[:, 1]], 1)                 # pos.zxy
+    w = pos.copy()
+    dr = np.ones(len(p), f32)
+    r = np.zeros(len(p), f32)
+    live = np.ones(len(p), bool)
+    with np.errstate(all="ignore"):
+        for _ in range(25):
+            rr = np.sqrt((w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1]) + w[:, 2] * w[:, 2]).astype(f32)
+            r = np.where(live, rr, r)
+            live = live & ~(r > f32(4))
+            x, y, z = w[:, 0], w[:, 1], w[:, 2]
+            x2 = x * x; x4 = x2 * x2; y2 = y * y; y4 = y2 * y2; z2 = z * z; z4 = z2 * z2
+            k3 = y2 + x2
+            k2 = (f32(1) / np.sqrt(k3 * k3 * k3 * k3 * k3 * k3 * k3)).astype(f32)
+            k1 = y4 + z4 + x4 - f32(6) * z2 * x2 - f32(6) * y2 * z2 + f32(2) * x2 * y2
+            k4 = y2 - z2 + x2
+            nx = f32(-8) * z * k4 * (y4 * y4 - f32(28) * y4 * y2 * x2 + f32(70) * y4 * x4 - f32(28) * y2 * x2 * x4 + x4 * x4) * k1 * k2
+            ny = f32(64) * y * z * x * (y2 - x2) * k4 * (y4 - f32(6) * y2 * x2 + x4) * k1 * k2
+            nz = f32(-16) * z2 * k3 * k4 * k4 + k1 * k1
+            nw = np.stack([nx, ny, nz], 1).astype(f32) + pos
+            r2 = r * r; r4 = r2 * r2
+            ndr = ((r4 * r2) * r) * f32(8) * dr + f32(1)
+            w = np.where(live[:, None], nw, w)
+            dr = np.where(live, ndr, dr).astype(f32)
+    return (f32(0.5) * O.glsl("log", r) * r / dr).astype(f32)
+
+
+def test_mandelbulb8_matches_numpy_restatement(O):
+    rng = np.random.RandomState(7)
+    pts = rng.uniform(-1.2, 1.2, size=(4000, 3)).astype(f32)
+    ref = _np_mandelbulb8(O, pts)
+    got = O.distance(O.SCENE_MB_POWER8, 0.0, pts)
+    ok = np.isfinite(ref)
+    assert ok.mean() > 0.99
+    assert np.array_equal(got[ok].view(np.uint32), ref[ok].view(np.uint32))
+
+
+def test_csg_scene_matches_numpy_restatement(O):
+    """fragment.shd:447-456 with libm exp/log in float64 — the deterministic built-ins are within
+    a few ulp, so values agree to ~1e-6."""
+    rng = np.random.RandomState(8)
+    p = rng.uniform(-1, 1, size=(3000, 3))
+    ln = lambda a, b: np.sqrt(a * a + b * b)
+    smin = lambda a, b, k: -np.log(np.exp(-k * a) + np.exp(-k * b)) / k
+    torus = lambda q: ln(ln(q[:, 0], q[:, 1]) - 0.85, q[:, 2]) - 0.1
+    box = lambda q, b: np.sqrt((np.maximum(np.abs(q) - np.array(b), 0) ** 2).sum(1)) - 0.03
+    d_sphere = np.sqrt((p * p).sum(1)) - 0.4
+    d_torus = smin(smin(torus(p), torus(p[:, [2, 0, 1]]), 64), torus(p[:, [1, 2, 0]]), 64)
+    d_box = smin(smin(box(p, (0.8, 0.06, 0.06)), box(p, (0.06, 0.8, 0.06)), 64), box(p, (0.06, 0.06, 0.8)), 64)
+    ref = smin(d_box, np.minimum(d_sphere, d_torus), 64)
+    got = O.distance(O.SCENE_TEST, 0.0, p.astype(f32))
+    assert np.allclose(got, ref, rtol=0, atol=3e-6)
+
+
+def test_cornell_de_matches_bruteforce(O):
+    """Cornell DE (fragment.shd:312-411) against a float64 closest-point-on-triangle search."""
+    v = O.cornell_vertices().astype(np.float64).reshape(32, 3, 3)
+    rng = np.random.RandomState(9)
+    pts = rng.uniform(-0.9, 0.9, size=(300, 3))
+
+    def tri_dist(p, a, b, c):
+        # Ericson, Real-Time Collision Detection §5.1.5
+        ab, ac, ap = b - a, c - a, p - a
+        d1, d2 = ab @ ap, ac @ ap
+        if d1 <= 0 and d2 <= 0: return np.linalg.norm(p - a)
+        bp = p - b; d3, d4 = ab @ bp, ac @ bp
+        if d3 >= 0 and d4 <= d3: return np.linalg.norm(p - b)
+        vc = d1 * d4 - d3 * d2
+        if vc <= 0 and d1 >= 0 and d3 <= 0: return np.linalg.norm(p - (a + ab * (d1 / (d1 - d3))))
+        cp = p - c; d5, d6 = ab @ cp, ac @ cp
+        if d6 >= 0 and d5 <= d6: return np.linalg.norm(p - c)
+        vb = d5 * d2 - d1 * d6
+        if vb <= 0 and d2 >= 0 and d6 <= 0: return np.linalg.norm(p - (a + ac * (d2 / (d2 - d6))))
+        va = d3 * d6 - d5 * d4
+        if va <= 0 and (d4 - d3) >= 0 and (d5 - d6) >= 0:
+            return np.linalg.norm(p - (b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6)))))
+        den = 1.0 / (va + vb + vc)
+        return np.linalg.norm(p - (a + ab * (vb * den) + ac * (vc * den)))
+
+    ref = np.array([min(tri_dist(p, *t) for t in v) for p in pts])
+    got = O.distance(O.SCENE_CORNELL, 0.0, pts.astype(f32))
+    assert np.allclose(got, ref, atol=2e-5)
+
+
+def test_julia_matches_numpy_restatement(O):
+    """Fractal2D.hs:63-98 again in numpy float32 (non-smooth: integers must agree exactly)."""
+    w, h, tick = 80, 48, 11.25
+    ft = f32(tick)
+    frac = lambda q: q - np.trunc(q)
+    a, b, c = frac(ft / f32(17)), frac(ft / f32(61)), frac(ft / f32(71))
+    two_pi = a * f32(2) * f32(np.pi)
+    jr = f32(np.sin(two_pi, dtype=f32)) * max(f32(0.7), b)
+    ji = f32(np.cos(two_pi, dtype=f32)) * max(f32(0.7), c)
+    fw, fh = f32(w), f32(h)
+    ratio = fw / fh
+    py, px = np.meshgrid(np.arange(h, dtype=f32), np.arange(w, dtype=f32), indexing="ij")
+    y = (py / fh) * f32(2.9) - f32(1.45)
+    x = (px / fw) * f32(2.9) * ratio - f32(1.45) * ratio
+    zr, zi = x.copy(), y.copy()
+    it = np.zeros((h, w), np.int32)
+    live = np.ones((h, w), bool)
+    for _ in range(40):
+        esc = (zr * zr + zi * zi) > f32(16)
+        live = live & ~esc
+        nr = (zr * zr - zi * zi) + jr
+        ni = (zr * zi + zi * zr) + ji
+        cyc = live & (nr == zr) & (ni == zi)
+        it = np.where(cyc, 40, it)
+        live = live & ~cyc
+        zr = np.where(live, nr, zr); zi = np.where(live, ni, zi)
+        it = np.where(live, it + 1, it)
+    ref = (np.trunc(it.astype(f32) / f32(40) * f32(255)).astype(np.uint32) << 8)
+    assert np.array_equal(O.julia(w, h, False, tick), ref)
+    sm = O.julia(w, h, True, tick)
+    assert (sm & 0xFFFF00FF == 0).all() and (sm >> 8 <= 255).all()
+    assert np.array_equal(sm[it == 40], ref[it == 40])          # interior = maxIter in both variants
+
+
+# ------------------------------------------------------------------ reference helpers
+def test_make_segments_edge_cases(O):
+    """makeNSegments, ConcurrentSegments.hs:14-23."""
+    assert O.make_segments(4, 5, 5) == []                        # low >= high
+    assert O.make_segments(0, 0, 10) == []                       # nsegc <= 0
+    assert O.make_segments(1, 3, 9) == [(3, 9)]
+    assert O.make_segments(3, 0, 10) == [(0, 3), (3, 6), (6, 10)]   # last takes the remainder
+    assert O.make_segments(8, 0, 3) == [(0, 1), (1, 2), (2, 3)]     # min(N, range) segments
+    assert O.make_segments(4, 2, 10) == [(2, 4), (4, 6), (6, 8), (8, 10)]
+    for n, lo, hi in [(7, 0, 100), (16, 3, 1080), (5, 0, 5)]:
+        segs = O.make_segments(n, lo, hi)
+        assert segs[0][0] == lo and segs[-1][1] == hi and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+
+
+def test_cube_pixel_to_dir_is_inverse_of_gl_face_selection(O):
+    """cubeMapPixelToDir (HDREnvMap.hs:76-87) vs the GL face table the sampler uses: sampling a cube
+    map at a texel-centre direction with NEAREST returns exactly that texel."""
+    w = 5
+    faces = np.arange(6 * w * w * 3, dtype=np.float32).reshape(6, w, w, 3)
+    faces = O.glsl("round_to_half", faces).reshape(faces.shape)
+    # render() cannot sample arbitrary directions, so check through the background: a 1×1 frame
+    # looks down the camera axis; instead verify the geometric inverse directly
+    for face in range(6):
+        for (x, y) in [(0, 0), (w - 1, 0), (2, 3), (w - 1, w - 1)]:
+            d = O.cube_pixel_to_dir(face, w, x, y)
+            ax = np.abs(d)
+            major = int(np.argmax(ax))
+            sel = major * 2 + (1 if d[major] < 0 else 0)
+            assert sel == face
+            sc, tc, ma = {0: (-d[2], -d[1], d[0]), 1: (d[2], -d[1], -d[0]), 2: (d[0], d[2], d[1]),
+                          3: (d[0], -d[2], -d[1]), 4: (d[0], -d[1], d[2]), 5: (-d[0], -d[1], -d[2])}[face]
+            i, j = int(np.floor(0.5 * (sc / ma + 1) * w)), int(np.floor(0.5 * (tc / ma + 1) * w))
+            assert (i, j) == (x, y)
+
+
+def test_test_latlong_envmap_and_cube(O):
+    """buildTestLatLongEnvMap (HDREnvMap.hs:55-73): six flat colours; every cube face of the
+    converted map is (away from the seams) its debug colour (:149-156 uses the same table)."""
+    env = O.test_latlong_envmap()
+    assert env.shape == (256, 512, 3)
+    cols = {tuple(c) for c in env.reshape(-1, 3)}
+    assert cols == {(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 0), (0, 1, 1)}
+    cube = O.latlong_to_cube(env)
+    assert cube.shape == (6, 170, 170, 3)
+    expect = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 0)]   # +X -X +Y -Y +Z(back) -Z(front)
+    for f in range(6):
+        centre = cube[f, 40:130, 40:130].reshape(-1, 3)
+        assert (centre == np.array(expect[f], np.float32)).all(), f
+
+
+def test_uffizi_fixture_and_rgbe(O, uffizi):
+    assert uffizi.shape == (256, 512, 3)
+    assert uffizi.max() == np.float32(15.9375)                     # 255·2^-4 (JuicyPixels: mantissa + 0.0)
+    assert np.allclose(uffizi.mean(axis=(0, 1)), [1.7846, 1.7548, 2.0330], atol=1e-3)
+    # toRGBE truncates v·(significand·255.9999/d) while toFloat adds 0.0: a write/read cycle of
+    # already-quantised data lands at most one mantissa step below (never above)
+    back = O.hdr_decode(O.hdr_encode(uffizi))
+    step = np.ldexp(np.float32(1), np.frexp(uffizi.max(axis=-1))[1] - 8)[..., None]
+    assert (back <= uffizi).all() and (uffizi - back <= step).all()
+    assert np.array_equal(back, O.rgbe_roundtrip(uffizi))
+    rt = O.rgbe_roundtrip(uffizi * np.float32(0.37))
+    rel = np.abs(rt - uffizi * np.float32(0.37)).max(axis=-1) / (uffizi * np.float32(0.37)).max(axis=-1)
+    assert rel.max() < 1.0 / 128.0                                 # 8-bit mantissa, truncated
+    assert O.rgbe_roundtrip(np.zeros((2, 3), f32)).sum() == 0
+
+
+def test_resize_and_convolve_properties(O, uffizi):
+    small = O.resize(uffizi, 256)
+    assert small.shape == (128, 256, 3)
+    assert np.allclose(small.mean(axis=(0, 1)), uffizi.mean(axis=(0, 1)), rtol=2e-3)
+    tiny = O.resize(uffizi, 32)
+    one = np.ones_like(tiny)
+    c1 = O.convolve(one, 1.0)
+    # constant map: Σ sinθ·c / n — linear in the input, same for every channel
+    assert np.allclose(c1[..., 0], c1[..., 1]) and np.allclose(O.convolve(one * 3, 1.0), c1 * 3, rtol=1e-5)
+    # higher powers are darker (cos^p <= cos for 0 <= cos <= 1)
+    assert (O.convolve(tiny, 8.0).sum() < O.convolve(tiny, 1.0).sum())
+
+
+def test_mip_resolve_and_screenshot(O):
+    fb = np.array([[0xFF000000, 0xFF0000FF], [0xFF00FF00, 0xFFFF0003]], np.uint32)
+    out = O.mip_resolve(fb, 1)
+    # per byte (a+b+c+d+2)>>2 : R (0+255+0+3+2)>>2=65, G (0+0+255+0+2)>>2=64, B 64, A 255
+    assert out.shape == (1, 1) and out[0, 0] == (0xFF << 24) | (64 << 16) | (64 << 8) | 65
+    rng = np.random.RandomState(3)
+    big = rng.randint(0, 2 ** 32, size=(16, 24), dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(O.mip_resolve(big, 2), O.mip_resolve(O.mip_resolve(big, 1), 1))
+    shot = O.screenshot_rows(fb)
+    assert shot.shape == (2, 2, 4) and (shot[..., 3] == 255).all()
+    assert tuple(shot[0, 0][:3]) == (0, 255, 0)                    # PNG row 0 = texture row h-1
+
+
+def test_render_rect_equals_crop_of_full_frame(O):
+    full = O.render(2, 96, 64, 0.0)
+    part = O.render(2, 96, 64, 0.0, rect=(32, 16, 80, 48))
+    assert np.array_equal(part["fb"], full["fb"][16:48, 32:80])
+    assert np.array_equal(part["hit"], full["hit"][16:48, 32:80])
+
+
+def test_camera_matches_reference_constants(O):
+    """in_time = 0: eye (0, 1.7071, 1.7071) for the orbit camera, (0, 0.4, -2) for Cornell."""
+    cam = O.camera(2, 0.0)
+    assert np.allclose(cam[9:], [0.0, 1.70710678, 1.70710678], atol=1e-6)
+    assert np.allclose(O.camera(0, 0.0)[9:], [0.0, 0.4, -2.0], atol=1e-7)
+    x, y, z = cam[0:3], cam[3:6], cam[6:9]
+    assert abs(np.dot(x, y)) < 1e-6 and abs(np.dot(y, z)) < 1e-6 and abs(np.linalg.norm(z) - 1) < 1e-6
