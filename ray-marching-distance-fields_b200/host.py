@@ -355,7 +355,7 @@ class ShaderRenderer:
     # -- Fractal2D.hs:63-98 --------------------------------------------------------------
     def juliaAnimated(self, w: int, h: int, fb, smooth: bool, tick: float, rows=None, resolve_log2: int = 0) -> np.ndarray:
         y0, y1 = rows if rows is not None else (0, h)
-        shape = ((y1 - y0) >> resolve_log2, w >> resolve_log2)
+        shape = (max(y1 - y0, 0) >> resolve_log2, max(w, 0) >> resolve_log2)
         if fb is None:
             fb = np.zeros(shape, np.uint32)
         assert fb.dtype == np.uint32 and fb.size == shape[0] * shape[1]
