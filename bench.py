@@ -236,9 +236,10 @@ def run_ours(args):
     sr.setStream(stream.cuda_stream)
 
     sharded = world > 1
+    grid, skew = par.balanced_grid(FB_W, FB_H, SPP_LOG2, world) if sharded else ((0, 0), 0)
     p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
                       shard_rank=rank if sharded else 0, shard_count=world if sharded else 1,
-                      layout=R.LAYOUT_PACKED_TILES if sharded else R.LAYOUT_FRAME)
+                      layout=R.LAYOUT_PACKED_TILES if sharded else R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew)
     n_out, n_tiles = sr.outputPixels(p)
     out_dev = torch.empty(n_out, dtype=torch.int32, device=dev)
     gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (sharded and rank == 0) else None
@@ -255,7 +256,7 @@ def run_ours(args):
     def step_resident():
         sr.renderDevice(p, out_dev.data_ptr())
         if sharded:
-            return par.gather_frame(out_dev, OUT_W, OUT_H, world, rank, gather_list)
+            return par.gather_frame(out_dev, OUT_W, OUT_H, world, rank, gather_list, grid, skew)
         return out_dev
 
     def step_e2e():
@@ -332,7 +333,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "scene": "FSMBPower8Shader", "in_time": TIME, "fb": [FB_W, FB_H], "out": [OUT_W, OUT_H],
-                       "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": "tiles(tx+ty mod %d)" % world,
+                       "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": ("tiles %dx%d, rank = (tx + %d*ty) mod %d, one NCCL gather" % (grid[0], grid[1], skew, world)) if sharded else "single GPU",
                        "l2": "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4},

@@ -66,7 +66,7 @@ enum { RMDF_OUT_RGBA8 = 0,     /* gamma-encoded 0xAABBGGRR, what the GL FBO hold
 enum { RMDF_LOD_QUAD = 0,      /* min=NEAREST/mag=LINEAR per 2×2 quad (GLHelpers.hs:105) */
        RMDF_LOD_ALWAYS_LINEAR = 1 };
 enum { RMDF_LAYOUT_FRAME = 0,  /* output indexed px + py·w over the whole frame          */
-       RMDF_LAYOUT_PACKED_TILES = 1 }; /* the rendered tiles back to back, ascending idx */
+       RMDF_LAYOUT_PACKED_TILES = 1 }; /* the rendered tiles back to back, ascending (ty, tx) */
 
 /* ---- lifetime: withShaderRenderer, ShaderRendering.hs:60-110 ------------------- */
 /* One context per GPU.  `device` is a CUDA ordinal.  Owns a stream, the five env-map
@@ -132,10 +132,13 @@ typedef struct {
     int32_t out_format;     /* RMDF_OUT_*  (RGBA32F requires resolve_log2 = 0) */
     int32_t mode;           /* RMDF_MODE_* */
     int32_t lod_policy;     /* RMDF_LOD_* */
-    int32_t shard_rank;     /* multi-GPU: render only the tiles of the 8×8 grid with   */
-    int32_t shard_count;    /*   (tx + ty) mod shard_count == shard_rank; count <= 1 = all */
+    int32_t shard_rank;     /* multi-GPU: render only the tiles (tx, ty) of the shard grid with */
+    int32_t shard_count;    /*   (tx + shard_skew·ty) mod shard_count == shard_rank; count <= 1 = all */
     int32_t layout;         /* RMDF_LAYOUT_* */
-    int32_t reserved[4];    /* must be 0 */
+    int32_t shard_grid_x;   /* shard grid; 0 = the reference's 8×8 tile grid with skew 1.  A finer   */
+    int32_t shard_grid_y;   /*   grid (e.g. 32×16, skew 2) balances the ranks better: the Mandelbulb's */
+    int32_t shard_skew;     /*   cost is concentrated mid-frame.  shard_grid_x % shard_count == 0.    */
+    int32_t reserved;       /* must be 0 */
 } rmdf_params;
 
 /* Number of 32-bit words (RGBA8) or float4 (RGBA32F) the call will write, and the

@@ -437,8 +437,8 @@ extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
 
 // ---- frame rendering ------------------------------------------------------------------
 struct WorkList {
-    bool full_frame;
-    unsigned long long mask;
+    int rect_mode;                    // 0 frame, 1 one tile, 2 shard
+    int tile_x0, tile_y0, shard_gx, shard_skew;
     int n_tiles, tile_w, tile_h;
     int64_t out_pixels;
     int out_stride;
@@ -455,35 +455,42 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     if (p->mode != RMDF_MODE_PARITY && p->mode != RMDF_MODE_FAST) return fail(RMDF_ERR_ARG, "mode %d unknown", p->mode);
     if (p->lod_policy != RMDF_LOD_QUAD && p->lod_policy != RMDF_LOD_ALWAYS_LINEAR) return fail(RMDF_ERR_ARG, "lod_policy %d unknown", p->lod_policy);
     if (p->layout != RMDF_LAYOUT_FRAME && p->layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", p->layout);
-    for (int i = 0; i < 4; i++) if (p->reserved[i]) return fail(RMDF_ERR_ARG, "reserved fields must be 0");
+    if (p->reserved) return fail(RMDF_ERR_ARG, "reserved field must be 0");
     const int k = p->resolve_log2, q = 1 << k;
     const bool sharded = p->shard_count > 1;
     if (sharded && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", p->shard_rank, p->shard_count);
-    if (p->shard_count > 64) return fail(RMDF_ERR_ARG, "shard_count %d > 64 tiles", p->shard_count);
-    wl->full_frame = (p->tile_idx < 0) && !sharded;
-    if (wl->full_frame) {
+    if (sharded && p->tile_idx >= 0) return fail(RMDF_ERR_ARG, "tile_idx and shard_count > 1 are mutually exclusive");
+    memset(wl, 0, sizeof *wl);
+    if (p->tile_idx < 0 && !sharded) {
         if ((p->fb_w % q) || (p->fb_h % q)) return fail(RMDF_ERR_ARG, "frame %dx%d is not a multiple of the %dx%d resolve footprint", p->fb_w, p->fb_h, q, q);
         if (p->layout != RMDF_LAYOUT_FRAME) return fail(RMDF_ERR_ARG, "packed layout needs tile_idx >= 0 or shard_count > 1");
-        wl->mask = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
+        wl->rect_mode = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
         wl->out_stride = p->fb_w >> k;
         wl->out_pixels = (int64_t)(p->fb_w >> k) * (p->fb_h >> k);
         return RMDF_OK;
     }
-    // 8×8 tile grid, ShaderRendering.hs:49-52,183-193.  Tile edges must fall on even
-    // pixel boundaries so that no 2×2 fragment quad straddles two tiles.
-    if ((p->fb_w % 16) || (p->fb_h % 16)) return fail(RMDF_ERR_UNSUPPORTED, "tiled rendering needs frame dimensions divisible by 16 (got %dx%d)", p->fb_w, p->fb_h);
-    wl->tile_w = p->fb_w / 8; wl->tile_h = p->fb_h / 8;
-    if ((wl->tile_w % q) || (wl->tile_h % q)) return fail(RMDF_ERR_ARG, "tile %dx%d is not a multiple of the %dx%d resolve footprint", wl->tile_w, wl->tile_h, q, q);
-    unsigned long long mask = 0;
-    for (int t = 0; t < 64; t++) {
-        const int tx = t & 7, ty = t >> 3;
-        bool sel = true;
-        if (p->tile_idx >= 0) sel = sel && (t == (p->tile_idx % 64));
-        if (sharded) sel = sel && (((tx + ty) % p->shard_count) == p->shard_rank);
-        if (sel) mask |= 1ull << t;
+    // Tile edges must fall on even pixel boundaries so that no 2×2 fragment quad straddles two tiles.
+    int gx = 8, gy = 8;                                   // ShaderRendering.hs:49-52
+    if (sharded) {
+        gx = p->shard_grid_x ? p->shard_grid_x : 8;
+        gy = p->shard_grid_y ? p->shard_grid_y : 8;
+        wl->shard_skew = p->shard_grid_x ? p->shard_skew : 1;
+        if (gx < 1 || gy < 1 || gx > 1024 || gy > 1024) return fail(RMDF_ERR_ARG, "shard grid %dx%d out of range", gx, gy);
+        if (gx % p->shard_count) return fail(RMDF_ERR_ARG, "shard_grid_x %d is not a multiple of shard_count %d", gx, p->shard_count);
+        if (wl->shard_skew < 0) return fail(RMDF_ERR_ARG, "shard_skew must be >= 0");
     }
-    wl->mask = mask;
-    wl->n_tiles = __builtin_popcountll(mask);
+    if ((p->fb_w % (2 * gx)) || (p->fb_h % (2 * gy)))
+        return fail(RMDF_ERR_UNSUPPORTED, "tiled rendering needs frame dimensions divisible by %dx%d (got %dx%d)", 2 * gx, 2 * gy, p->fb_w, p->fb_h);
+    wl->tile_w = p->fb_w / gx; wl->tile_h = p->fb_h / gy;
+    if ((wl->tile_w % q) || (wl->tile_h % q)) return fail(RMDF_ERR_ARG, "tile %dx%d is not a multiple of the %dx%d resolve footprint", wl->tile_w, wl->tile_h, q, q);
+    if (sharded) {
+        wl->rect_mode = 2; wl->shard_gx = gx;
+        wl->n_tiles = gy * (gx / p->shard_count);
+    } else {
+        const int t = p->tile_idx % 64;                   // idx `mod` nTiles, :186-188
+        wl->rect_mode = 1; wl->n_tiles = 1;
+        wl->tile_x0 = (t & 7) * wl->tile_w; wl->tile_y0 = (t >> 3) * wl->tile_h;
+    }
     if (p->layout == RMDF_LAYOUT_PACKED_TILES) {
         wl->out_stride = wl->tile_w >> k;
         wl->out_pixels = (int64_t)wl->n_tiles * (wl->tile_w >> k) * (wl->tile_h >> k);
@@ -527,10 +534,11 @@ static void make_camera(int scene, float in_time, float cam[12])
 
 static int pick_item_h(int64_t blocks_of_32_rows, int resident_warps, int k)
 {
-    // shrink the work item until there are ≥ 4 items per resident warp (small frames)
+    // shrink the work item until there are ≥ 16 items per resident warp: small frames fill the
+    // machine, and a rank's share of a sharded frame ends without a long tail
     int item_h = 32;
     const int min_h = (1 << k) > 4 ? (1 << k) : 4;
-    while (item_h > min_h && blocks_of_32_rows * (32 / item_h) < (int64_t)resident_warps * 4) item_h >>= 1;
+    while (item_h > min_h && blocks_of_32_rows * (32 / item_h) < (int64_t)resident_warps * 16) item_h >>= 1;
     return item_h;
 }
 
@@ -559,8 +567,9 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.bsphere_r = (p->scene == RMDF_SCENE_MB_POWER8) ? 1.15f : (p->scene == RMDF_SCENE_MB_GENERAL) ? 1.5f : 1.0f;
     mp.lod_policy = p->lod_policy; mp.resolve_log2 = p->resolve_log2;
     mp.out_format = p->out_format; mp.layout = p->layout;
-    mp.full_frame = wl.full_frame ? 1 : 0;
-    mp.tile_mask = wl.mask; mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
+    mp.rect_mode = wl.rect_mode; mp.tile_x0 = wl.tile_x0; mp.tile_y0 = wl.tile_y0;
+    mp.shard_gx = wl.shard_gx; mp.shard_count = p->shard_count; mp.shard_rank = p->shard_rank; mp.shard_skew = wl.shard_skew;
+    mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
     mp.out_stride = wl.out_stride;
     for (int s = 0; s < RMDF_ENV_SLOTS; s++) {
         mp.env_point[s] = ctx->env[s].tex_point;
@@ -608,7 +617,7 @@ extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
     const size_t px_bytes = (p->out_format == RMDF_OUT_RGBA32F) ? 16 : 4;
     const size_t bytes = (size_t)wl.out_pixels * px_bytes;
     if ((rc = ensure_staging(ctx, bytes))) return rc;
-    const bool partial = !wl.full_frame && p->layout == RMDF_LAYOUT_FRAME;
+    const bool partial = wl.rect_mode != 0 && p->layout == RMDF_LAYOUT_FRAME;
     if (partial)   // drawShaderTile leaves the rest of the FBO untouched: start from the caller's pixels
         CU(cudaMemcpyAsync(ctx->d_out, fb_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = rmdf_render_device(ctx, p, ctx->d_out))) return rc;

@@ -21,9 +21,11 @@ struct MarchParams {
     float power;                      // animated Mandelbulb power (fragment.shd:116-119)
     float bsphere_r;                  // fragment.shd:640-649
     int   lod_policy, resolve_log2, out_format, layout;
-    // work list: either the whole frame or a subset of the reference's 8×8 tile grid
-    int   full_frame;
-    unsigned long long tile_mask;
+    // work list: the whole frame (0), one tile of the reference's 8×8 grid (1), or this rank's
+    // tiles of the shard grid (2): (tx + skew·ty) mod count == rank, packed by ascending (ty, tx)
+    int   rect_mode;
+    int   tile_x0, tile_y0;           // rect_mode 1: origin of the tile
+    int   shard_gx, shard_count, shard_rank, shard_skew;
     int   tile_w, tile_h;             // level-0 size of one tile
     int   item_h;                     // rows per work item: 4, 8, 16 or 32
     int   blocks_x, blocks_y;         // 32×item_h blocks per rect

@@ -1,46 +1,75 @@
-"""Multi-GPU frame rendering: one process per GPU, tiles of the reference's 8×8 grid
-(ShaderRendering.hs:49-52) dealt to ranks by (tx + ty) mod G, each rank renders its tiles
-packed back to back, and rank 0 gathers them over NCCL (torch.distributed) and reassembles
-the frame.  There is no data-path collective besides that gather."""
+"""Multi-GPU frame rendering: one process per GPU.  The frame is cut into a shard grid of
+gx × gy tiles (default: the reference's 8×8 grid, ShaderRendering.hs:49-52); tile (tx, ty)
+belongs to rank (tx + skew·ty) mod G, each rank renders its tiles packed back to back in
+ascending (ty, tx) order, and rank 0 gathers them with ONE collective (torch.distributed
+gather over NCCL) and reassembles the frame.  Samples are independent, so there is no other
+data-path communication.
+
+A finer grid with a skew balances the ranks: the Mandelbulb's cost is concentrated mid-frame
+(measured with the oracle's counters: 8×8 skew 1 → 90 % at G = 8; 32×16 skew 2 → 97 %)."""
 from __future__ import annotations
 
 import numpy as np
 
-
-def tiles_of_rank(rank: int, count: int):
-    """Tile ids (ty·8 + tx) rendered by `rank`, ascending — the packed order."""
-    return [t for t in range(64) if ((t & 7) + (t >> 3)) % count == rank]
+DEFAULT_GRID = (8, 8)
+DEFAULT_SKEW = 1
 
 
-def tile_permutation(count: int) -> np.ndarray:
+def balanced_grid(fb_w: int, fb_h: int, resolve_log2: int, world: int):
+    """Finest shard grid ≤ 32×32 that keeps tiles on even pixel boundaries, a multiple of the
+    resolve footprint and gx a multiple of the world size; skew 2 (1 for two ranks)."""
+    q = 1 << resolve_log2
+    def pick(dim, need_mult):
+        for g in (32, 16, 8):
+            if g % need_mult == 0 and dim % (2 * g) == 0 and (dim // g) % q == 0:
+                return g
+        raise ValueError("no shard grid fits dimension %d" % dim)
+    return (pick(fb_w, world), pick(fb_h, 1)), (1 if world == 2 else 2)
+
+
+def tiles_of_rank(rank: int, count: int, grid=DEFAULT_GRID, skew: int = DEFAULT_SKEW):
+    """Tile ids (ty·gx + tx) rendered by `rank`, in packed order."""
+    gx, gy = grid
+    return [ty * gx + tx for ty in range(gy) for tx in range(gx) if (tx + skew * ty) % count == rank]
+
+
+def tile_permutation(count: int, grid=DEFAULT_GRID, skew: int = DEFAULT_SKEW) -> np.ndarray:
     """perm[t] = index of tile t inside the concatenation of all ranks' packed outputs."""
-    perm = np.empty(64, np.int64)
+    gx, gy = grid
+    perm = np.empty(gx * gy, np.int64)
     pos = 0
     for r in range(count):
-        for t in tiles_of_rank(r, count):
+        for t in tiles_of_rank(r, count, grid, skew):
             perm[t] = pos
             pos += 1
     return perm
 
 
-def assemble_tiles_numpy(packed_per_rank, w: int, h: int, count: int) -> np.ndarray:
+def assemble_tiles_numpy(packed_per_rank, w: int, h: int, count: int, grid=DEFAULT_GRID, skew: int = DEFAULT_SKEW) -> np.ndarray:
     """packed_per_rank[r]: flat uint32 array of rank r's tiles → [h, w] frame (row 0 = bottom)."""
-    tw, th = w // 8, h // 8
+    gx, gy = grid
+    tw, th = w // gx, h // gy
     allt = np.concatenate([np.asarray(p).reshape(-1, th, tw) for p in packed_per_rank], axis=0)
-    tiles = allt[tile_permutation(count)]                      # [64, th, tw] in tile-id order
-    return tiles.reshape(8, 8, th, tw).transpose(0, 2, 1, 3).reshape(h, w)
+    tiles = allt[tile_permutation(count, grid, skew)]          # [gy·gx, th, tw] in tile-id order
+    return tiles.reshape(gy, gx, th, tw).transpose(0, 2, 1, 3).reshape(h, w)
 
 
-def assemble_tiles_torch(gathered, w: int, h: int, count: int):
+_perm_cache = {}
+
+
+def assemble_tiles_torch(gathered, w: int, h: int, count: int, grid=DEFAULT_GRID, skew: int = DEFAULT_SKEW):
     """Same on the GPU: gathered = [count, tiles_per_rank·th·tw] int32 tensor on rank 0."""
     import torch
-    tw, th = w // 8, h // 8
-    perm = torch.as_tensor(tile_permutation(count), device=gathered.device)
-    tiles = gathered.reshape(64, th, tw).index_select(0, perm)
-    return tiles.reshape(8, 8, th, tw).permute(0, 2, 1, 3).reshape(h, w)
+    gx, gy = grid
+    tw, th = w // gx, h // gy
+    key = (count, grid, skew, str(gathered.device))
+    if key not in _perm_cache:
+        _perm_cache[key] = torch.as_tensor(tile_permutation(count, grid, skew), device=gathered.device)
+    tiles = gathered.reshape(gx * gy, th, tw).index_select(0, _perm_cache[key])
+    return tiles.reshape(gy, gx, th, tw).permute(0, 2, 1, 3).reshape(h, w)
 
 
-def gather_frame(packed, w: int, h: int, world: int, rank: int, gather_list=None):
+def gather_frame(packed, w: int, h: int, world: int, rank: int, gather_list=None, grid=DEFAULT_GRID, skew: int = DEFAULT_SKEW):
     """Rank-local packed tiles (1-D int32 tensor, CUDA+NCCL or CPU+gloo) → the [h, w] frame on
     rank 0 (None elsewhere).  One gather, no other collective."""
     import torch
@@ -52,4 +81,4 @@ def gather_frame(packed, w: int, h: int, world: int, rank: int, gather_list=None
     dist.gather(packed, gather_list if rank == 0 else None, dst=0)
     if rank != 0:
         return None
-    return assemble_tiles_torch(torch.stack(gather_list), w, h, world)
+    return assemble_tiles_torch(torch.stack(gather_list), w, h, world, grid, skew)

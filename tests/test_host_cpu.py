@@ -70,10 +70,13 @@ def test_output_sizing_and_validation(R):
     # errors: every one sets rmdf_last_error
     for bad in (dict(scene=4), dict(fb_w=0), dict(resolve_log2=4), dict(out_format=2), dict(mode=7), dict(lod_policy=3),
                 dict(out_format=R.OUT_RGBA32F, resolve_log2=1), dict(fb_w=250, resolve_log2=2), dict(fb_w=100, fb_h=100, tile_idx=0),
-                dict(shard_count=2, shard_rank=2), dict(layout=R.LAYOUT_PACKED_TILES), dict(shard_count=65, shard_rank=0)):
+                dict(shard_count=2, shard_rank=2), dict(layout=R.LAYOUT_PACKED_TILES), dict(shard_count=3, shard_rank=0),
+                dict(shard_count=2, tile_idx=1), dict(shard_count=2, shard_grid_x=7, shard_grid_y=8), dict(shard_count=2, shard_grid_x=64, shard_grid_y=8, fb_w=320)):
         assert n(**bad) == -1, bad
         assert len(L.rmdf_last_error()) > 0
-    p = _params(R); p.reserved[1] = 1
+    assert n(shard_count=4, shard_rank=1, shard_grid_x=32, shard_grid_y=16, shard_skew=2, layout=R.LAYOUT_PACKED_TILES) == 256 * 128 // 4
+    assert nt.value == 32 * 16 // 4
+    p = _params(R); p.reserved = 1
     assert L.rmdf_render_output_pixels(C.byref(p), None) == -1
     assert L.rmdf_render_output_pixels(None, None) == -1
 
@@ -133,15 +136,19 @@ def test_tile_dealing_and_assembly(R):
     from importlib import import_module
     par = import_module("ray-marching-distance-fields_b200.parallel")
     for g in (1, 2, 4, 8):
-        owned = [par.tiles_of_rank(r, g) for r in range(g)]
-        assert sorted(sum(owned, [])) == list(range(64)) and all(len(o) == 64 // g for o in owned)
-        # every rank holds tiles from every tile row and (g = 8) every column: balanced load
-        assert all(len({t >> 3 for t in o}) == 8 for o in owned)
-        w, h = 64, 32
-        frame = np.arange(w * h, dtype=np.uint32).reshape(h, w)
-        tiles = frame.reshape(8, h // 8, 8, w // 8).transpose(0, 2, 1, 3).reshape(64, h // 8, w // 8)
-        packed = [tiles[o].reshape(-1) for o in owned]
-        assert np.array_equal(par.assemble_tiles_numpy(packed, w, h, g), frame)
+        for grid, skew in (((8, 8), 1), ((32, 16), 2), ((16, 8), 3)):
+            gx, gy = grid
+            owned = [par.tiles_of_rank(r, g, grid, skew) for r in range(g)]
+            assert sorted(sum(owned, [])) == list(range(gx * gy)) and all(len(o) == gx * gy // g for o in owned)
+            # every rank holds tiles from every tile row: balanced load
+            assert all(len({t // gx for t in o}) == gy for o in owned)
+            w, h = 128, 64
+            frame = np.arange(w * h, dtype=np.uint32).reshape(h, w)
+            tiles = frame.reshape(gy, h // gy, gx, w // gx).transpose(0, 2, 1, 3).reshape(gx * gy, h // gy, w // gx)
+            packed = [tiles[o].reshape(-1) for o in owned]
+            assert np.array_equal(par.assemble_tiles_numpy(packed, w, h, g, grid, skew), frame)
+    assert par.balanced_grid(15360, 8640, 2, 8) == ((32, 16), 2)
+    assert par.balanced_grid(15360, 8640, 2, 2) == ((32, 16), 1)
 
 
 _GLOO_WORKER = r'''
@@ -154,9 +161,10 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=world)
 w, h = 128, 64
 frame = (np.arange(w * h, dtype=np.int64) * 2654435761 % (1 << 31)).astype(np.int32).reshape(h, w)
-tiles = frame.reshape(8, h // 8, 8, w // 8).transpose(0, 2, 1, 3).reshape(64, -1)
-mine = torch.from_numpy(np.ascontiguousarray(tiles[par.tiles_of_rank(rank, world)]).reshape(-1))
-out = par.gather_frame(mine, w, h, world, rank)
+grid, skew = (16, 8), 2
+tiles = frame.reshape(8, h // 8, 16, w // 16).transpose(0, 2, 1, 3).reshape(128, -1)
+mine = torch.from_numpy(np.ascontiguousarray(tiles[par.tiles_of_rank(rank, world, grid, skew)]).reshape(-1))
+out = par.gather_frame(mine, w, h, world, rank, grid=grid, skew=skew)
 if rank == 0:
     assert out is not None and np.array_equal(out.numpy(), frame), "assembled frame differs"
     print("GLOO_OK")

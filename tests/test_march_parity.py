@@ -109,17 +109,27 @@ def test_in_kernel_resolve_equals_mip_chain(sr, O, R, oracle_envs, k):
 
 
 @pytest.mark.parametrize("count", [2, 4, 8])
-def test_shards_partition_the_frame(sr, R, oracle_envs, count):
-    """Multi-GPU decomposition on one GPU: the packed tiles of all ranks reassemble the frame."""
+@pytest.mark.parametrize("grid", [None, ((16, 8), 2), ((32, 16), 2), ((8, 32), 3)])
+def test_shards_partition_the_frame(sr, R, oracle_envs, count, grid):
+    """Multi-GPU decomposition on one GPU: the packed tiles of all ranks reassemble the frame,
+    for the reference's 8×8 grid and for finer skewed shard grids."""
     from importlib import import_module
     par = import_module("ray-marching-distance-fields_b200.parallel")
     _bind(sr, oracle_envs)
-    w, h, k = 256, 128, 1
+    w, h, k = 512, 256, 1
+    g, skew = grid if grid else (par.DEFAULT_GRID, par.DEFAULT_SKEW)
+    kw = dict(shard_grid=g, shard_skew=skew) if grid else {}
     full = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
     packed = [sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k,
-                                shard_rank=r, shard_count=count, layout=R.LAYOUT_PACKED_TILES) for r in range(count)]
-    frame = par.assemble_tiles_numpy(packed, w >> k, h >> k, count)
+                                shard_rank=r, shard_count=count, layout=R.LAYOUT_PACKED_TILES, **kw) for r in range(count)]
+    frame = par.assemble_tiles_numpy(packed, w >> k, h >> k, count, g, skew)
     assert np.array_equal(frame, full)
+    # frame layout: each rank fills only its own tiles of a shared-size buffer
+    acc = np.zeros_like(full)
+    for r in range(count):
+        acc |= sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k,
+                                 shard_rank=r, shard_count=count, **kw)
+    assert np.array_equal(acc, full)
 
 
 def test_fast_mode_within_tolerance(sr, O, R, oracle_envs):
