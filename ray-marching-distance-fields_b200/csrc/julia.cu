@@ -24,7 +24,7 @@ __device__ __forceinline__ uint32_t j_box4(uint32_t a, uint32_t b, uint32_t c, u
     return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
 }
 
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, 8)
 julia_kernel(const JuliaParams P)
 {
     __shared__ __align__(16) uint32_t s_stage[kWarpsPerCta][kBlockDim * kBlockDim];

@@ -10,11 +10,15 @@ namespace rmdf {
 struct MathFast {
     static constexpr bool kFast = true;
 #ifndef RMDF_FAST_MIN_CTAS
-#define RMDF_FAST_MIN_CTAS 2
+#define RMDF_FAST_MIN_CTAS 6      // x 4 warps = 24 warps/SM, 80 registers
 #endif
 #ifndef RMDF_FAST_DE_NOINLINE
 #define RMDF_FAST_DE_NOINLINE 0
 #endif
+#ifndef RMDF_FAST_MARCH_NOINLINE
+#define RMDF_FAST_MARCH_NOINLINE 0
+#endif
+    static constexpr bool kNoinlineMarch = RMDF_FAST_MARCH_NOINLINE;
     static constexpr int  kMinCtas = RMDF_FAST_MIN_CTAS;
     static constexpr bool kNoinlineDE = RMDF_FAST_DE_NOINLINE;
     static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }

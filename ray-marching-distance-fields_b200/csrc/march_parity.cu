@@ -9,11 +9,15 @@ namespace rmdf {
 struct MathParity {
     static constexpr bool kFast = false;
 #ifndef RMDF_MIN_CTAS
-#define RMDF_MIN_CTAS 3      // 80 registers, 24 warps/SM: measured 62.8 → 54.1 ms on config 4
+#define RMDF_MIN_CTAS 6      // x 4 warps = 24 warps/SM, 80 registers
 #endif
 #ifndef RMDF_DE_NOINLINE
 #define RMDF_DE_NOINLINE 1   // measured 73.3 → 62.8 ms (instruction-cache misses)
 #endif
+#ifndef RMDF_MARCH_NOINLINE
+#define RMDF_MARCH_NOINLINE 0
+#endif
+    static constexpr bool kNoinlineMarch = RMDF_MARCH_NOINLINE;
     static constexpr int  kMinCtas = RMDF_MIN_CTAS;
     static constexpr bool kNoinlineDE = RMDF_DE_NOINLINE;
     static __device__ __forceinline__ float sqrt(float x) { return rg_sqrt(x); }

@@ -7,7 +7,10 @@
 namespace rmdf {
 
 constexpr int kBlockDim     = 32;    // a work item is a 32×32 block of frame-buffer samples
-constexpr int kWarpsPerCta  = 8;
+#ifndef RMDF_WARPS_PER_CTA
+#define RMDF_WARPS_PER_CTA 4   // small CTAs: register/shared-memory occupancy in steps of 4 warps
+#endif
+constexpr int kWarpsPerCta  = RMDF_WARPS_PER_CTA;
 constexpr int kCtaThreads   = kWarpsPerCta * 32;
 constexpr int kCornellF4    = 32 * 6; // 32 triangles × 6 float4 of precomputed terms
 
