@@ -327,6 +327,12 @@ def run_ours(args):
         flops = algorithmic_flops(frame_cnt)
         samples = FB_W * FB_H
         ach_tf = flops / (kernel_ms * 1e-3) / 1e12 / world               # per-GPU rate
+        traffic = None
+        try:                                                             # from the committed ncu capture (per launch, N = 1)
+            tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())[mode_name]
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if world == 1 else None
+        except Exception:
+            pass
         alg_bytes = OUT_W * OUT_H * 4 + sum(6 * c_.shape[1] ** 2 * 8 for c_ in cubes)    # resolved frame + half4 texels
         line = {
             "metric": "mandelbulb_4k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
@@ -341,7 +347,7 @@ def run_ours(args):
             "sdf_steps_per_s": (frame_cnt["march_de"] + frame_cnt["shade_de"]) / (ms_res * 1e-3),
             "frame_counters": {k: int(v) for k, v in frame_cnt.items()},
             "roofline": {"bound": "fp32_fma", "achieved": ach_tf, "peak": fp32_peak["tflops"], "unit": "TFLOP/s",
-                         "frac": ach_tf / fp32_peak["tflops"], "traffic": None,
+                         "frac": ach_tf / fp32_peak["tflops"], "traffic": traffic,
                          "peak_source": "in-run FFMA-chain microbenchmark (148 SM x 128 lanes x 2 x clock); MEASURED_PEAKS.json carries no FP32 figure",
                          "algorithmic_flop_per_frame": flops, "kernel_ms": kernel_ms,
                          "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
