@@ -369,6 +369,130 @@ def run_ours(args):
     return 0
 
 
+# ---- secondary workload: BASELINE.json configs[4], the 2D Julia set ---------------------------
+J_OUT_W, J_OUT_H, J_SPP_LOG2, J_TICK = 7680, 4320, 3, 7.0          # 64 spp = 8×8 ordered grid
+J_FB_W, J_FB_H = J_OUT_W << J_SPP_LOG2, J_OUT_H << J_SPP_LOG2      # 61440 × 34560 samples
+J_WORKLOAD = "Julia set 7680x4320 x64spp (FB 61440x34560), juliaAnimated tick 7, plain colouring"
+F_JULIA_ITER = 13.0                                                # flop per iteration, SURVEY.md §8d
+
+
+def julia_cpu_baseline(steps: int = 1, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12"))):
+    """The CPU restatement of Fractal2D.hs on all host threads over 135 row slabs spread uniformly
+    over the 34560 rows (forSegmentsConcurrently-style row split inside each slab)."""
+    from oracle import oracle as O
+    def run(rows_per_slab):
+        n, t0 = 0, time.perf_counter()
+        for i in range(135):
+            y0 = i * 256
+            O.julia(J_FB_W, J_FB_H, False, J_TICK, rows=(y0, y0 + rows_per_slab))
+            n += rows_per_slab * J_FB_W
+        return n, time.perf_counter() - t0
+    n, dt = run(32)                                   # probe (32 rows keep every host thread busy)
+    rows = int(max(32, min(256, (n / dt) * budget_s / (135 * J_FB_W))))
+    times = []
+    for _ in range(max(1, steps)):
+        n, dt = run(rows); times.append(dt)
+    dt = float(np.mean(times))
+    return {"value": n / dt, "unit": "samples/s", "cores": O.host_threads(), "kind": "port",
+            "sample": "135 slabs of %d rows x 61440 samples spread over the frame (%.2f%% of it), C restatement of Fractal2D.hs with OpenMP — not GHC"
+                      % (rows, 100.0 * n / (J_FB_W * J_FB_H)), "seconds_per_step": dt}
+
+
+def run_julia(args):
+    import torch
+    import torch.distributed as dist
+    import rmdf_b200 as R
+    from importlib import import_module
+    par = import_module("ray-marching-distance-fields_b200.parallel")
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            b = julia_cpu_baseline(steps=args.steps)
+            print(json.dumps({"impl": "reference", "metric": "julia_8k_samples_per_s", "value": b["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": b["seconds_per_step"] * 1e3, "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": J_WORKLOAD},
+                              "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                              "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — librmdf_b200 has no CPU fallback")
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sr = R.ShaderRenderer(local)
+    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); sr.setStream(stream.cuda_stream)
+    band_h = par.julia_band_height(J_FB_H, J_SPP_LOG2, world)
+    n_out = J_OUT_W * J_OUT_H // world
+    out_dev = torch.empty(n_out, dtype=torch.int32, device=dev)
+    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    frame_host = torch.empty(J_OUT_H * J_OUT_W, dtype=torch.int32).pin_memory() if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        sr.juliaBandsDevice(J_FB_W, J_FB_H, False, J_TICK, J_SPP_LOG2, band_h, rank, world, out_dev.data_ptr())
+        return par.gather_bands(out_dev, J_OUT_W, J_OUT_H, world, rank, band_h >> J_SPP_LOG2, gather_list)
+
+    def step_e2e():
+        frame = step_resident()
+        if rank == 0:
+            frame_host.copy_(frame.reshape(-1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def timed(fn, k, w, events):
+        for _ in range(w):
+            flush.zero_(); fn()
+        ms = []
+        for _ in range(k):
+            flush.zero_(); barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter(); e0.record(stream); fn(); e1.record(stream); barrier()
+            ms.append(e0.elapsed_time(e1) if events else (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    sr.resetCounters()
+    ms_res = timed(step_resident, args.steps, args.warmup, True)
+    c = sr.counters()
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1, False)
+    its = torch.tensor([c["inner_iters"] / (args.steps + args.warmup)], dtype=torch.float64, device=dev)
+    kt = torch.tensor([c["last_kernel_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(its, op=dist.ReduceOp.SUM); dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak = sr.measureFp32Peak()["tflops"]
+        samples = J_FB_W * J_FB_H
+        ach = float(its.item()) * F_JULIA_ITER / (float(kt.item()) * 1e-3) / 1e12 / world
+        line = {"metric": "julia_8k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": J_WORKLOAD, "fb": [J_FB_W, J_FB_H], "out": [J_OUT_W, J_OUT_H], "spp": 64,
+                                                "parallelism": ("row bands of %d rows, band b -> rank b mod %d, one NCCL gather" % (band_h, world)) if world > 1 else "single GPU",
+                                                "l2": "flushed between steps (256 MiB write)"},
+                "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 64,
+                        "d2h_bytes_per_step": J_OUT_W * J_OUT_H * 4},
+                "gpu_launches": args.steps, "iterations_per_frame": int(its.item()),
+                "roofline": {"bound": "fp32_fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                             "kernel_ms": float(kt.item()), "note": "13 flop per z <- z^2 + c iteration; ncu: ALU pipe (compares, counters) is the busiest, see profiles/r1_julia_v2.md"},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            b = julia_cpu_baseline()
+            line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    sr.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,8 +502,12 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "parity", "fast"],
                     help="auto: the fast build if it meets BASELINE's tolerance against the parity build in this run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
+                    help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "julia8k" and (args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus == 1):
+        return run_julia(args)
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -388,7 +516,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
         return subprocess.call(cmd)
-    return run_ours(args)
+    return run_julia(args) if args.workload == "julia8k" else run_ours(args)
 
 
 if __name__ == "__main__":

@@ -244,9 +244,11 @@ def make_segments(nseg: int, low: int, high: int):
 # ---------------------------------------------------------------- julia / frame buffer
 def julia(w: int, h: int, smooth: bool, tick: float, rows=None, threads: int = 0) -> np.ndarray:
     y0, y1 = rows if rows is not None else (0, h)
-    fb = np.zeros((h, w), np.uint32)
-    lib().oracle_julia(w, h, fb.ctypes.data_as(C.POINTER(C.c_uint32)), int(smooth), C.c_double(tick), y0, y1, threads)
-    return fb[y0:y1]
+    fb = np.zeros((y1 - y0, w), np.uint32)
+    # the C function indexes px + py·w with absolute py: hand it the address row 0 would have
+    base = C.cast(C.c_void_p(fb.ctypes.data - y0 * w * 4), C.POINTER(C.c_uint32))
+    lib().oracle_julia(w, h, base, int(smooth), C.c_double(tick), y0, y1, threads)
+    return fb
 
 
 def mip_resolve(fb: np.ndarray, levels: int) -> np.ndarray:

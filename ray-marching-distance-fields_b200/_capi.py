@@ -23,7 +23,7 @@ EXPORTS = [
     "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device",
     "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
-    "rmdf_julia", "rmdf_julia_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak",
+    "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak",
 ]
 
 
@@ -91,6 +91,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_render_device.argtypes = [vp, PP, vp]
     L.rmdf_julia.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_julia_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp]
+    L.rmdf_julia_bands_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_mip_resolve_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.rmdf_counters_reset.argtypes = [vp]

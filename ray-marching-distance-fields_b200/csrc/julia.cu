@@ -28,12 +28,17 @@ __global__ void __launch_bounds__(kCtaThreads, 8)
 julia_kernel(const JuliaParams P)
 {
     __shared__ __align__(16) uint32_t s_stage[kWarpsPerCta][kBlockDim * kBlockDim];
+    __shared__ uint32_t s_lut[41];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *stage = s_stage[warp];
+    // plain variant: the pixel word is a function of the iteration count alone,
+    // toGreen . truncate $ fromIntegral iCnt / 40 * 255  (Fractal2D.hs:93-97)
+    if (threadIdx.x < 41) s_lut[threadIdx.x] = ((uint32_t)(int)truncf((float)threadIdx.x / 40.0f * 255.0f)) << 8;
+    __syncthreads();
     const int mx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
     const int my = ((lane >> 1) & 1) | ((lane >> 2) & 2);
     const int k = P.resolve_log2;
-    const float log2_inv_den = rg_log(2.0f);
+    const float log_2 = rg_log(2.0f);
     unsigned iters = 0, samples = 0;
 
     for (;;) {
@@ -41,44 +46,53 @@ julia_kernel(const JuliaParams P)
         if (lane == 0) item = atomicAdd(P.queue, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= (unsigned)P.n_items) break;
-        const int by = (int)item / P.blocks_x, bx = (int)item - by * P.blocks_x;
-        const int rh = P.y1 - P.y0;
-        const int bw = min(kBlockDim, P.w - bx * kBlockDim), bh = min(P.item_h, rh - by * P.item_h);
-        const int X0 = bx * kBlockDim, Y0 = P.y0 + by * P.item_h;
+        // item → (band of this rank, block row inside the band, block column)
+        const int per_band = P.blocks_x * P.blocks_y;
+        const int band_k = (int)item / per_band, in_band = (int)item - band_k * per_band;
+        const int by = in_band / P.blocks_x, bx = in_band - by * P.blocks_x;
+        const int band = band_k * P.shard_count + P.shard_rank;
+        const int bw = min(kBlockDim, P.w - bx * kBlockDim), bh = min(P.item_h, P.band_h - by * P.item_h);
+        const int X0 = bx * kBlockDim, Y0 = P.y0 + band * P.band_h + by * P.item_h;
+
+        // x depends on the column only (Fractal2D.hs:82): four columns per lane and block
+        float xs[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) xs[c] = ((float)(X0 + c * 8 + mx) / P.fw) * 2.9f * P.ratio - P.xshift;
 
 #pragma unroll 1
-        for (int tile = 0; tile < P.item_h; tile++) {
-            const int tx = (tile & 3) * 8, ty = (tile >> 2) * 4;
-            if (tx >= bw || ty >= bh) continue;
-            const int lx = tx + mx, ly = ty + my;
-            if (lx < bw && ly < bh) {
-                const float fpx = (float)(X0 + lx), fpy = (float)(Y0 + ly);
-                const float y = (fpy / P.fh) * 2.9f - 1.45f;                 // :81
-                const float x = (fpx / P.fw) * 2.9f * P.ratio - P.xshift;    // :82
-                float zr = x, zi = y;
-                int iter = 0;
-                for (;;) {                                                    // go, :85-90
-                    if (iter == 40 || (zr * zr + zi * zi) > 4.0f * 4.0f) break;
-                    const float nr = (zr * zr - zi * zi) + P.julia_r;
-                    const float ni = (zr * zi + zi * zr) + P.julia_i;
-                    if (nr == zr && ni == zi) { iter = 40; break; }           // 1-cycle detection
-                    zr = nr; zi = ni;
-                    iter++;
-                    iters++;
-                }
-                float val;
-                if (P.smooth) {
-                    float ic = 40.0f;
-                    if (iter != 40) {
-                        const float v = (float)iter - rg_log(rg_log(zr * zr + zi * zi)) / log2_inv_den;
-                        ic = v > 0.0f ? v : 0.0f;
+        for (int trow = 0; trow < (P.item_h >> 2); trow++) {
+            const int ty = trow * 4;
+            if (ty >= bh) break;
+            const int ly = ty + my;
+            const float y = ((float)(Y0 + ly) / P.fh) * 2.9f - 1.45f;               // :81
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int lx = c * 8 + mx;
+                if (c * 8 >= bw) break;                                             // warp-uniform
+                if (lx < bw && ly < bh) {
+                    float zr = xs[c], zi = y;
+                    int iter = 0;
+                    for (;;) {                                                       // go, :85-90
+                        const float zr2 = zr * zr, zi2 = zi * zi;
+                        if (iter == 40 || (zr2 + zi2) > 4.0f * 4.0f) break;
+                        const float nr = (zr2 - zi2) + P.julia_r;
+                        const float ni = (zr * zi + zi * zr) + P.julia_i;
+                        if (nr == zr && ni == zi) { iter = 40; break; }              // 1-cycle detection
+                        zr = nr; zi = ni;
+                        iter++;
                     }
-                    val = ic / 40.0f * 255.0f;
-                } else {
-                    val = (float)iter / 40.0f * 255.0f;
+                    iters += (unsigned)iter;
+                    uint32_t word;
+                    if (P.smooth && iter != 40) {
+                        const float v = (float)iter - rg_log(rg_log(zr * zr + zi * zi)) / log_2;
+                        const float ic = v > 0.0f ? v : 0.0f;
+                        word = ((uint32_t)(int)truncf(ic / 40.0f * 255.0f)) << 8;
+                    } else {
+                        word = s_lut[iter];
+                    }
+                    stage[ly * kBlockDim + lx] = word;                               // toGreen, :93-94
+                    samples++;
                 }
-                stage[ly * kBlockDim + lx] = ((uint32_t)(int)truncf(val)) << 8;   // toGreen, :93-94
-                samples++;
             }
         }
         __syncwarp();
@@ -92,7 +106,7 @@ julia_kernel(const JuliaParams P)
             __syncwarp();
         }
         const int ow = bw >> k, oh = bh >> k;
-        const long long o0 = (long long)((Y0 - P.y0) >> k) * P.out_stride + (X0 >> k);
+        const long long o0 = ((long long)band_k * (P.band_h >> k) + ((by * P.item_h) >> k)) * P.out_stride + (X0 >> k);
         const bool vec_ok = ((ow & 3) == 0) && ((P.out_stride & 3) == 0) && ((o0 & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
         if (vec_ok) {

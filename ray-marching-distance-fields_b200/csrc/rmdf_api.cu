@@ -627,13 +627,20 @@ extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
 }
 
 // ---- Julia ---------------------------------------------------------------------------------
-static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int y0, int y1, int k, JuliaParams *jp)
+static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int y0, int y1, int k,
+                        int band_h, int shard_rank, int shard_count, JuliaParams *jp)
 {
     if (w < 1 || h < 1 || w > 131072 || h > 131072) return fail(RMDF_ERR_ARG, "julia frame %dx%d out of range", w, h);
     if (k < 0 || k > 3) return fail(RMDF_ERR_ARG, "resolve_log2 %d out of range [0,3]", k);
     const int q = 1 << k;
     if (y0 < 0 || y1 > h || y0 >= y1) return fail(RMDF_ERR_ARG, "julia rows [%d,%d) outside [0,%d)", y0, y1, h);
     if ((w % q) || (y0 % q) || (y1 % q)) return fail(RMDF_ERR_ARG, "julia width/rows must be multiples of %d", q);
+    if (shard_count < 1) shard_count = 1;
+    if (shard_rank < 0 || shard_rank >= shard_count) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", shard_rank, shard_count);
+    if (shard_count == 1 && band_h <= 0) band_h = y1 - y0;
+    if (band_h <= 0 || (band_h % q) || ((y1 - y0) % band_h)) return fail(RMDF_ERR_ARG, "band height %d must divide the %d rows and be a multiple of %d", band_h, y1 - y0, q);
+    const int n_bands = (y1 - y0) / band_h;
+    if (n_bands % shard_count) return fail(RMDF_ERR_ARG, "%d bands do not split evenly over %d ranks", n_bands, shard_count);
     memset(jp, 0, sizeof *jp);
     // Fractal2D.hs:65-76 (host, libm like GHC's Float primops)
     const float pi = 3.14159265358979323846f;
@@ -644,16 +651,18 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->julia_r = sinf(two_pi) * (0.7f > st2 ? 0.7f : st2);
     jp->julia_i = cosf(two_pi) * (0.7f > st3 ? 0.7f : st3);
     jp->w = w; jp->h = h; jp->y0 = y0; jp->y1 = y1; jp->smooth = smooth ? 1 : 0; jp->resolve_log2 = k;
+    jp->band_h = band_h; jp->shard_rank = shard_rank; jp->shard_count = shard_count;
     jp->fw = (float)w; jp->fh = (float)h;
     jp->ratio = jp->fw / jp->fh;
     jp->xshift = 1.45f * jp->ratio;
+    const int my_bands = n_bands / shard_count;
     const int ctas = julia_ctas_per_sm();
     const int resident_warps = ctas * ctx->sm_count * kWarpsPerCta;
     const int bx = (w + kBlockDim - 1) / kBlockDim;
-    jp->item_h = pick_item_h((int64_t)bx * ((y1 - y0 + 31) / 32), resident_warps, k);
+    jp->item_h = pick_item_h((int64_t)bx * ((band_h + 31) / 32) * my_bands, resident_warps, k);
     jp->blocks_x = bx;
-    jp->blocks_y = (y1 - y0 + jp->item_h - 1) / jp->item_h;
-    const int64_t n = (int64_t)jp->blocks_x * jp->blocks_y;
+    jp->blocks_y = (band_h + jp->item_h - 1) / jp->item_h;
+    const int64_t n = (int64_t)jp->blocks_x * jp->blocks_y * my_bands;
     if (n > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "julia frame too large");
     jp->n_items = (int)n;
     jp->out_stride = w >> k;
@@ -662,13 +671,8 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     return RMDF_OK;
 }
 
-extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
-                                 int y0, int y1, int resolve_log2, void *fb_dev)
+static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
-    if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
-    JuliaParams jp;
-    if ((rc = julia_params(ctx, w, h, smooth, tick, y0, y1, resolve_log2, &jp))) return rc;
     jp.out = (uint32_t *)fb_dev;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     int grid = julia_ctas_per_sm() * ctx->sm_count;
@@ -682,6 +686,26 @@ extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double
     ctx->ev_valid = true;
     ctx->launches++;
     return RMDF_OK;
+}
+
+extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
+                                 int y0, int y1, int resolve_log2, void *fb_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    JuliaParams jp;
+    if ((rc = julia_params(ctx, w, h, smooth, tick, y0, y1, resolve_log2, 0, 0, 1, &jp))) return rc;
+    return julia_launch(ctx, jp, fb_dev);
+}
+
+extern "C" int rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int resolve_log2,
+                                       int band_h, int shard_rank, int shard_count, void *fb_dev)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    JuliaParams jp;
+    if ((rc = julia_params(ctx, w, h, smooth, tick, 0, h, resolve_log2, band_h, shard_rank, shard_count, &jp))) return rc;
+    return julia_launch(ctx, jp, fb_dev);
 }
 
 extern "C" int rmdf_julia(rmdf_ctx *ctx, int w, int h, int smooth, double tick,

@@ -82,3 +82,43 @@ def gather_frame(packed, w: int, h: int, world: int, rank: int, gather_list=None
     if rank != 0:
         return None
     return assemble_tiles_torch(torch.stack(gather_list), w, h, world, grid, skew)
+
+
+# ---- Julia: interleaved row bands (the reference splits rows, Fractal2D.hs:98) -----------------
+def julia_band_height(h: int, resolve_log2: int, world: int, min_bands_per_rank: int = 8) -> int:
+    """Largest band height that is a multiple of 32 rows (one work-item row) and of the resolve
+    footprint, divides h, and leaves every rank at least `min_bands_per_rank` bands."""
+    q = max(32, 1 << resolve_log2)
+    best = None
+    for bh in range(q, h + 1, q):
+        if h % bh == 0 and (h // bh) % world == 0 and (h // bh) // world >= min_bands_per_rank:
+            best = bh
+    if best is None:
+        for bh in range(1 << resolve_log2, h + 1, 1 << resolve_log2):
+            if h % bh == 0 and (h // bh) % world == 0:
+                best = bh if best is None else best
+    if best is None:
+        raise ValueError("no band height fits h=%d for %d ranks" % (h, world))
+    return best
+
+
+def assemble_bands_numpy(packed_per_rank, w: int, h: int, count: int, band_h: int) -> np.ndarray:
+    """packed_per_rank[r]: rank r's bands (b ≡ r mod count, ascending) → [h, w] (resolved sizes)."""
+    nb = h // band_h // count
+    allb = np.stack([np.asarray(p).reshape(nb, band_h, w) for p in packed_per_rank], axis=1)   # [nb, count, band_h, w]
+    return allb.reshape(h, w)
+
+
+def gather_bands(packed, w: int, h: int, world: int, rank: int, band_h: int, gather_list=None):
+    """torch version with one gather to rank 0 (None elsewhere); w, h, band_h in output pixels."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return packed.reshape(h, w)
+    if rank == 0 and gather_list is None:
+        gather_list = [torch.empty_like(packed) for _ in range(world)]
+    dist.gather(packed, gather_list if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    nb = h // band_h // world
+    return torch.stack(gather_list).reshape(world, nb, band_h, w).permute(1, 0, 2, 3).reshape(h, w)

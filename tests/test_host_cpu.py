@@ -147,6 +147,10 @@ def test_tile_dealing_and_assembly(R):
             tiles = frame.reshape(gy, h // gy, gx, w // gx).transpose(0, 2, 1, 3).reshape(gx * gy, h // gy, w // gx)
             packed = [tiles[o].reshape(-1) for o in owned]
             assert np.array_equal(par.assemble_tiles_numpy(packed, w, h, g, grid, skew), frame)
+    assert par.julia_band_height(34560, 3, 8) == 480 and par.julia_band_height(34560, 3, 1) % 32 == 0
+    bands = [np.full((2, 4, 6), r) for r in range(3)]          # 3 ranks × 2 bands × 4 rows × 6 px
+    fr = par.assemble_bands_numpy([b.reshape(-1) for b in bands], 6, 24, 3, 4)
+    assert fr[:, 0].tolist() == [0] * 4 + [1] * 4 + [2] * 4 + [0] * 4 + [1] * 4 + [2] * 4
     assert par.balanced_grid(15360, 8640, 2, 8) == ((32, 16), 2)
     assert par.balanced_grid(15360, 8640, 2, 2) == ((32, 16), 1)
 

@@ -40,6 +40,25 @@ def test_julia_rows_and_resolve(sr, O):
     assert c["samples"] > 0 and c["inner_iters"] > 0
 
 
+@pytest.mark.parametrize("count", [1, 2, 4, 8])
+def test_julia_bands_partition_the_frame(sr, O, count):
+    """Multi-GPU decomposition on one GPU: interleaved row bands of all ranks reassemble the frame."""
+    import torch
+    from importlib import import_module
+    par = import_module("ray-marching-distance-fields_b200.parallel")
+    w, h, k = 512, 1024, 2
+    band_h = par.julia_band_height(h, k, count, min_bands_per_rank=2)
+    assert h % band_h == 0 and (h // band_h) % count == 0
+    want = O.mip_resolve(O.julia(w, h, False, 7.0), k)
+    packed = []
+    for r in range(count):
+        out = torch.zeros((h >> k) // count * (w >> k), dtype=torch.int32, device="cuda")
+        sr.juliaBandsDevice(w, h, False, 7.0, k, band_h, r, count, out.data_ptr()); sr.sync()
+        packed.append(out.cpu().numpy().view(np.uint32))
+    got = par.assemble_bands_numpy(packed, w >> k, h >> k, count, band_h >> k)
+    assert np.array_equal(got, want)
+
+
 def test_julia_errors(sr, R):
     with pytest.raises(R.RmdfError):
         sr.juliaAnimated(100, 100, None, False, 0.0, resolve_log2=3)        # 100 % 8 != 0
