@@ -240,9 +240,31 @@ def run_ours(args):
     p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
                       shard_rank=rank if sharded else 0, shard_count=world if sharded else 1,
                       layout=R.LAYOUT_PACKED_TILES if sharded else R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew)
+    # N > 1: by default the gather is fused into the kernel — every rank stores its resolved tiles
+    # straight into rank 0's frame buffer over NVLink (parallel.SharedFrame); --gather nccl keeps
+    # the packed-tiles + dist.gather + re-assembly path
+    shared = None
+    if sharded and args.gather == "peer":
+        try:
+            shared = par.SharedFrame(sr, OUT_W * OUT_H, world, rank)
+            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
+                              shard_rank=rank, shard_count=world, layout=R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew)
+        except R.RmdfError as e:                                   # no peer access on this box
+            if rank == 0:
+                print("bench.py: peer frame buffer unavailable (%s); using the NCCL gather" % e, file=sys.stderr)
+            shared = None
+    ok = torch.tensor([1 if (shared is not None or not sharded or args.gather != "peer") else 0], device=dev)
+    if sharded:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if args.gather == "peer" and int(ok.item()) == 0 and shared is not None:
+            shared.close(); shared = None
+        if shared is None:
+            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
+                              shard_rank=rank, shard_count=world, layout=R.LAYOUT_PACKED_TILES, shard_grid=grid, shard_skew=skew)
     n_out, n_tiles = sr.outputPixels(p)
-    out_dev = torch.empty(n_out, dtype=torch.int32, device=dev)
-    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (sharded and rank == 0) else None
+    out_dev = torch.empty(n_out if shared is None else 1, dtype=torch.int32, device=dev)
+    shared_frame = shared.as_tensor() if (shared is not None and rank == 0) else None
+    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (sharded and rank == 0 and shared is None) else None
     frame_host = torch.empty(OUT_H * OUT_W, dtype=torch.int32).pin_memory() if rank == 0 else None
     cubes_pinned = [torch.from_numpy(c).pin_memory() for c in cubes]
     h2d_bytes = sum(c.numel() * 4 for c in cubes_pinned) + 64          # cube maps + rmdf_params
@@ -254,6 +276,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if shared is not None:
+            sr.renderDevice(p, shared.ptr)                              # tile stores land on rank 0
+            shared.complete()                                           # one barrier, no data-path collective
+            return shared_frame
         sr.renderDevice(p, out_dev.data_ptr())
         if sharded:
             return par.gather_frame(out_dev, OUT_W, OUT_H, world, rank, gather_list, grid, skew)
@@ -303,8 +329,10 @@ def run_ours(args):
                        dtype=torch.float64, device=dev)
     kms = []
     for _ in range(3):
-        flush.zero_(); sr.renderDevice(p, out_dev.data_ptr()); torch.cuda.synchronize()
+        flush.zero_(); sr.renderDevice(p, shared.ptr if shared is not None else out_dev.data_ptr()); torch.cuda.synchronize()
         kms.append(sr.counters()["last_kernel_ms"])
+    if sharded:
+        dist.barrier()
     kt = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -339,7 +367,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "scene": "FSMBPower8Shader", "in_time": TIME, "fb": [FB_W, FB_H], "out": [OUT_W, OUT_H],
-                       "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": ("tiles %dx%d, rank = (tx + %d*ty) mod %d, one NCCL gather" % (grid[0], grid[1], skew, world)) if sharded else "single GPU",
+                       "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": ("tiles %dx%d, rank = (tx + %d*ty) mod %d, %s" % (grid[0], grid[1], skew, world, "tile stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if sharded else "single GPU",
                        "l2": "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4},
@@ -502,6 +530,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "parity", "fast"],
                     help="auto: the fast build if it meets BASELINE's tolerance against the parity build in this run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-memory stores (default) or NCCL gather")
     ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
                     help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")
     args = ap.parse_args()

@@ -170,6 +170,21 @@ int  rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, double tic
  * image already on the device. */
 int  rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w, int h, int levels, void *out_dev);
 
+/* ---- multi-GPU: one frame buffer that every rank's kernel writes into ------------ */
+/* The gather of a sharded frame fused into the march kernel's store phase: rank 0 owns the
+ * (resolved) frame buffer, the other ranks map it and pass it as `fb_dev` with
+ * RMDF_LAYOUT_FRAME + shard_* — their 128-bit tile stores then travel over NVLink while the
+ * rest of the frame is still being marched; only a barrier remains afterwards.  (No
+ * counterpart in the reference, which is single-GPU.)
+ * rmdf_shared_alloc: cudaMalloc on ctx's device + an IPC handle (64 opaque bytes) to send to
+ * the other processes; rmdf_shared_open: map such a handle on ctx's device (peer access over
+ * NVLink/PCIe); rmdf_enable_peer: the same-process equivalent for a second context. */
+int  rmdf_shared_alloc(rmdf_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char handle[64]);
+int  rmdf_shared_free(rmdf_ctx *ctx, void *dev_ptr);
+int  rmdf_shared_open(rmdf_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int  rmdf_shared_close(rmdf_ctx *ctx, void *dev_ptr);
+int  rmdf_enable_peer(rmdf_ctx *ctx, int peer_device);
+
 /* ---- counters (new; the reference only prints FPS, App.hs:221-238) ------------- */
 typedef struct {
     uint64_t samples;       /* rays generated                                   */

@@ -736,6 +736,56 @@ extern "C" int rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w,
     return RMDF_OK;
 }
 
+// ---- multi-GPU shared frame buffer ------------------------------------------------------------
+extern "C" int rmdf_shared_alloc(rmdf_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char handle[64])
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!dev_ptr || !handle || bytes <= 0) return fail(RMDF_ERR_ARG, "rmdf_shared_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(RMDF_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *dev_ptr = p;
+    return RMDF_OK;
+}
+extern "C" int rmdf_shared_free(rmdf_ctx *ctx, void *dev_ptr)
+{
+    int rc = use(ctx); if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaFree(dev_ptr));
+    return RMDF_OK;
+}
+extern "C" int rmdf_shared_open(rmdf_ctx *ctx, const unsigned char handle[64], void **dev_ptr)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!dev_ptr || !handle) return fail(RMDF_ERR_ARG, "rmdf_shared_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RMDF_OK;
+}
+extern "C" int rmdf_shared_close(rmdf_ctx *ctx, void *dev_ptr)
+{
+    int rc = use(ctx); if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return RMDF_OK;
+}
+extern "C" int rmdf_enable_peer(rmdf_ctx *ctx, int peer_device)
+{
+    int rc = use(ctx); if (rc) return rc;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return fail(RMDF_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    return RMDF_OK;
+}
+
 // ---- measurement ----------------------------------------------------------------------------
 extern "C" int rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz)
 {

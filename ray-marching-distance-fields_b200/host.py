@@ -371,6 +371,28 @@ class ShaderRenderer:
         check(self._lib.rmdf_julia_bands_device(self._h, w, h, int(bool(smooth)), C.c_double(tick), resolve_log2, band_h,
                                                 shard_rank, shard_count, C.c_void_p(dev_ptr)))
 
+    # -- multi-GPU shared frame buffer ------------------------------------------------------
+    def sharedAlloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of a buffer other processes' kernels can write into."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(self._lib.rmdf_shared_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def sharedFree(self, ptr: int) -> None:
+        check(self._lib.rmdf_shared_free(self._h, C.c_void_p(ptr)))
+
+    def sharedOpen(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        check(self._lib.rmdf_shared_open(self._h, handle, C.byref(ptr)))
+        return int(ptr.value)
+
+    def sharedClose(self, ptr: int) -> None:
+        check(self._lib.rmdf_shared_close(self._h, C.c_void_p(ptr)))
+
+    def enablePeer(self, peer_device: int) -> None:
+        check(self._lib.rmdf_enable_peer(self._h, peer_device))
+
     # -- counters ------------------------------------------------------------------------
     def counters(self) -> dict:
         c = Counters()

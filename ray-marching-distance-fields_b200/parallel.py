@@ -122,3 +122,46 @@ def gather_bands(packed, w: int, h: int, world: int, rank: int, band_h: int, gat
         return None
     nb = h // band_h // world
     return torch.stack(gather_list).reshape(world, nb, band_h, w).permute(1, 0, 2, 3).reshape(h, w)
+
+
+# ---- fused gather: every rank's kernel stores its tiles straight into rank 0's frame buffer ----
+class SharedFrame:
+    """The resolved frame buffer lives on rank 0's GPU; the other ranks map it through CUDA IPC and
+    pass `self.ptr` as the render target (LAYOUT_FRAME + shard_*), so the march kernel's 128-bit
+    tile stores cross NVLink while the rest of the frame is still being marched.  After the launch
+    only a barrier is needed (`complete()`): there is no separate gather or re-assembly pass."""
+
+    def __init__(self, sr, n_words: int, world: int, rank: int):
+        import torch.distributed as dist
+        self.sr, self.world, self.rank, self.n_words = sr, world, rank, n_words
+        box = [None]
+        if rank == 0:
+            self.ptr, handle = sr.sharedAlloc(n_words * 4)
+            box[0] = handle
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                self.ptr = sr.sharedOpen(box[0])
+
+    def complete(self):
+        """All ranks' stores are in rank 0's memory once this returns on rank 0's stream."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+
+    def as_tensor(self):
+        """Rank 0: a torch int32 view of the frame (no copy)."""
+        import torch
+        assert self.rank == 0
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (self.n_words,), "typestr": "<i4", "data": (self.ptr, False), "version": 3}
+        return torch.as_tensor(w, device="cuda")
+
+    def close(self):
+        if self.rank == 0:
+            self.sr.sharedFree(self.ptr)
+        elif self.world > 1:
+            self.sr.sharedClose(self.ptr)

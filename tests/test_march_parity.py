@@ -132,6 +132,35 @@ def test_shards_partition_the_frame(sr, R, oracle_envs, count, grid):
     assert np.array_equal(acc, full)
 
 
+def test_peer_frame_buffer_two_gpus(R, oracle_envs):
+    """The fused gather: a second GPU's kernel stores its tiles straight into GPU 0's frame buffer
+    (peer memory); together with GPU 0's own tiles the frame is bit-identical to a single-GPU render.
+    Needs two devices (run with gpurun --gpus 2); skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w, h, k = 1024, 512, 2
+    with R.ShaderRenderer(0) as a, R.ShaderRenderer(1) as b:
+        for r in (a, b):
+            for s in range(5):
+                r.bindCubeMap(s, oracle_envs[s])
+        want = a.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+        b.enablePeer(0)
+        ptr, _handle = a.sharedAlloc((w >> k) * (h >> k) * 4)
+        for rank, r in enumerate((a, b)):
+            p = r.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k, shard_rank=rank, shard_count=2,
+                             shard_grid=(16, 8), shard_skew=1)
+            r.renderDevice(p, ptr)
+        a.sync(); b.sync()
+        class _W:
+            pass
+        wv = _W()
+        wv.__cuda_array_interface__ = {"shape": ((h >> k) * (w >> k),), "typestr": "<i4", "data": (ptr, False), "version": 3}
+        got = torch.as_tensor(wv, device="cuda:0").cpu().numpy().view(np.uint32).reshape(h >> k, w >> k)
+        a.sharedFree(ptr)
+    assert np.array_equal(got, want)
+
+
 def test_fast_mode_within_tolerance(sr, O, R, oracle_envs):
     """Fast mode (FMA contraction, MUFU, HW filtering) vs the oracle at BASELINE's tolerance."""
     _bind(sr, oracle_envs)
