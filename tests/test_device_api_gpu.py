@@ -1,0 +1,70 @@
+"""Device-pointer entry points of the C ABI (what a host that keeps frames on the GPU calls):
+rmdf_render_device + rmdf_set_stream + rmdf_mip_resolve_device + rmdf_envmap_convolve_device,
+driven with torch tensors as plain device memory."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_render_device_on_caller_stream_and_mip_chain(sr, O, R, oracle_envs):
+    import torch
+    for s in range(5):
+        sr.bindCubeMap(s, oracle_envs[s])
+    w, h = 512, 256
+    stream = torch.cuda.Stream()
+    sr.setStream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            lvl0 = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sr.renderDevice(p, lvl0.data_ptr())                    # asynchronous on the caller's stream
+            e1.record(stream)
+            outs = {}
+            for k in (1, 2, 3):
+                outs[k] = torch.zeros((w >> k) * (h >> k), dtype=torch.int32, device="cuda")
+                R._capi.check(sr._lib.rmdf_mip_resolve_device(sr.handle, lvl0.data_ptr(), w, h, k, outs[k].data_ptr()))
+        stream.synchronize()
+        assert e0.elapsed_time(e1) > 0.0                           # the kernel really ran on that stream
+        ref = O.render(2, w, h, 0.0, envs=oracle_envs)["fb"]
+        assert np.array_equal(lvl0.cpu().numpy().view(np.uint32).reshape(h, w), ref)
+        for k in (1, 2, 3):
+            got = outs[k].cpu().numpy().view(np.uint32).reshape(h >> k, w >> k)
+            assert np.array_equal(got, O.mip_resolve(ref, k)), k
+            # … and the standalone chain equals the in-kernel resolve
+            assert np.array_equal(got, sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k))
+    finally:
+        sr.setStream(None)
+    with pytest.raises(R.RmdfError):
+        R._capi.check(sr._lib.rmdf_mip_resolve_device(sr.handle, None, w, h, 1, None))
+
+
+def test_convolve_device_pointers(sr, O, R, uffizi):
+    import torch
+    small = O.resize(uffizi, 64)
+    src = torch.from_numpy(small).cuda()
+    out = torch.zeros((2,) + small.shape, dtype=torch.float32, device="cuda")
+    pw = (C.c_float * 2)(1.0, 8.0)
+    R._capi.check(sr._lib.rmdf_envmap_convolve_device(sr.handle, src.data_ptr(), small.shape[1], small.shape[0], pw, 2, out.data_ptr()))
+    sr.sync()
+    got = out.cpu().numpy()
+    assert np.allclose(got[0], O.convolve(small, 1.0), rtol=1e-4) and np.allclose(got[1], O.convolve(small, 8.0), rtol=1e-4)
+    assert sr.counters()["last_kernel_ms"] > 0.0
+
+
+def test_counters_accumulate_and_reset(sr, R):
+    sr.resetCounters()
+    sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0)
+    a = sr.counters()
+    sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0)
+    b = sr.counters()
+    assert a["samples"] == 64 * 64 and b["samples"] == 2 * 64 * 64 and b["march_de"] == 2 * a["march_de"]
+    assert b["launches"] == a["launches"] + 1
+    sr.resetCounters()
+    assert sr.counters()["samples"] == 0
+    pk = sr.measureFp32Peak()
+    assert 30.0 < pk["tflops"] < 90.0                              # 148 SM × 128 lanes × 2 × ~1.9 GHz ≈ 72
