@@ -65,6 +65,11 @@ enum { RMDF_OUT_RGBA8 = 0,     /* gamma-encoded 0xAABBGGRR, what the GL FBO hold
        RMDF_OUT_RGBA32F = 1 }; /* linear pre-gamma RGB + hit flag in A (test/inspection) */
 enum { RMDF_LOD_QUAD = 0,      /* min=NEAREST/mag=LINEAR per 2×2 quad (GLHelpers.hs:105) */
        RMDF_LOD_ALWAYS_LINEAR = 1 };
+/* Switches that exist in fragment.shd but are OFF in the reference's build.
+ * Each is bit-identical to the oracle with the same switch; none changes the default path. */
+enum { RMDF_FLAG_NORMAL_CENTRAL = 1,    /* normal_central_difference (fragment.shd:471-480) instead of :463-470 */
+       RMDF_FLAG_CAM_ORTHO = 2,         /* #define CAM_ORTHO (fragment.shd:906-908, 853-861), width 2 */
+       RMDF_FLAG_RAY_TRACING_TEST = 4 };/* #define RAY_TRACING_TEST (fragment.shd:915-937): ray-traced Cornell box */
 enum { RMDF_LAYOUT_FRAME = 0,  /* output indexed px + py·w over the whole frame          */
        RMDF_LAYOUT_PACKED_TILES = 1 }; /* the rendered tiles back to back, ascending (ty, tx) */
 
@@ -138,7 +143,7 @@ typedef struct {
     int32_t shard_grid_x;   /* shard grid; 0 = the reference's 8×8 tile grid with skew 1.  A finer   */
     int32_t shard_grid_y;   /*   grid (e.g. 32×16, skew 2) balances the ranks better: the Mandelbulb's */
     int32_t shard_skew;     /*   cost is concentrated mid-frame.  shard_grid_x % shard_count == 0.    */
-    int32_t reserved;       /* must be 0 */
+    int32_t flags;          /* RMDF_FLAG_*; 0 = the shader exactly as the reference builds it */
 } rmdf_params;
 
 /* Number of 32-bit words (RGBA8) or float4 (RGBA32F) the call will write, and the

@@ -12,6 +12,10 @@ enum { ORACLE_SCENE_CORNELL = 0, ORACLE_SCENE_TEST = 1, ORACLE_SCENE_MB_POWER8 =
 /* texture-unit order of srEnvCubeMaps, ShaderRendering.hs:86-91,173-174 */
 enum { ORACLE_ENV_REFLECTION = 0, ORACLE_ENV_COS_1 = 1, ORACLE_ENV_COS_8 = 2, ORACLE_ENV_COS_64 = 3, ORACLE_ENV_COS_512 = 4 };
 enum { ORACLE_LOD_QUAD = 0, ORACLE_LOD_ALWAYS_LINEAR = 1 };
+/* compile-time switches of the shader that are OFF in the reference */
+enum { ORACLE_FLAG_NORMAL_CENTRAL = 1,   /* normal_central_difference, fragment.shd:471-480 (unused at :751) */
+       ORACLE_FLAG_CAM_ORTHO = 2,        /* #define CAM_ORTHO, fragment.shd:906-908, 853-861 */
+       ORACLE_FLAG_RAY_TRACING_TEST = 4  /* #define RAY_TRACING_TEST, fragment.shd:915-937 (Cornell geometry) */ };
 
 typedef struct {
     int32_t scene;            /* ORACLE_SCENE_* */
@@ -19,6 +23,7 @@ typedef struct {
     float   time;             /* in_time */
     int32_t lod_policy;       /* ORACLE_LOD_* */
     int32_t threads;          /* 0 = all */
+    int32_t flags;            /* ORACLE_FLAG_*; 0 = the reference's build */
     int32_t env_face[5];      /* cube face width per slot; 0 = constant 1.0 */
     const float *env[5];      /* 6·w·w·3 floats (RGB16F values widened), faces +X,-X,+Y,-Y,+Z,-Z */
     const float *cornell;     /* 96·3 floats (cornell_geom texels) */

@@ -19,12 +19,13 @@ _LIB_PATH = _HERE / "_build" / "liboracle.so"
 SCENE_CORNELL, SCENE_TEST, SCENE_MB_POWER8, SCENE_MB_GENERAL = 0, 1, 2, 3
 ENV_REFLECTION, ENV_COS_1, ENV_COS_8, ENV_COS_64, ENV_COS_512 = range(5)
 LOD_QUAD, LOD_ALWAYS_LINEAR = 0, 1
+FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST = 1, 2, 4
 
 
 class _Frame(C.Structure):
     _fields_ = [
         ("scene", C.c_int32), ("fb_w", C.c_int32), ("fb_h", C.c_int32), ("time", C.c_float),
-        ("lod_policy", C.c_int32), ("threads", C.c_int32),
+        ("lod_policy", C.c_int32), ("threads", C.c_int32), ("flags", C.c_int32),
         ("env_face", C.c_int32 * 5), ("env", C.POINTER(C.c_float) * 5),
         ("cornell", C.POINTER(C.c_float)),
     ]
@@ -116,7 +117,7 @@ def distance(scene: int, time: float, pts: np.ndarray) -> np.ndarray:
 
 
 def render(scene: int, fb_w: int, fb_h: int, time: float = 0.0, envs=None, rect=None,
-           lod_policy: int = LOD_QUAD, threads: int = 0, want_linear: bool = True):
+           lod_policy: int = LOD_QUAD, threads: int = 0, want_linear: bool = True, flags: int = 0):
     """fragment.shd main() for every pixel of rect = (x0, y0, x1, y1) (default: full frame).
 
     envs: None (all slots constant 1.0 = "no env lighting") or a list of 5
@@ -126,7 +127,7 @@ def render(scene: int, fb_w: int, fb_h: int, time: float = 0.0, envs=None, rect=
     """
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, fb_w, fb_h)
     f = _Frame()
-    f.scene, f.fb_w, f.fb_h, f.time, f.lod_policy, f.threads = scene, fb_w, fb_h, time, lod_policy, threads
+    f.scene, f.fb_w, f.fb_h, f.time, f.lod_policy, f.threads, f.flags = scene, fb_w, fb_h, time, lod_policy, threads, flags
     keep = []
     for s in range(5):
         e = None if envs is None else envs[s]

@@ -17,6 +17,7 @@ MODE_PARITY, MODE_FAST = 0, 1
 OUT_RGBA8, OUT_RGBA32F = 0, 1
 LOD_QUAD, LOD_ALWAYS_LINEAR = 0, 1
 LAYOUT_FRAME, LAYOUT_PACKED_TILES = 0, 1
+FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST = 1, 2, 4
 
 EXPORTS = [
     "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
@@ -34,7 +35,7 @@ class Params(C.Structure):
         ("scene", C.c_int32), ("fb_w", C.c_int32), ("fb_h", C.c_int32), ("time", C.c_float),
         ("tile_idx", C.c_int32), ("resolve_log2", C.c_int32), ("out_format", C.c_int32), ("mode", C.c_int32),
         ("lod_policy", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("layout", C.c_int32),
-        ("shard_grid_x", C.c_int32), ("shard_grid_y", C.c_int32), ("shard_skew", C.c_int32), ("reserved", C.c_int32),
+        ("shard_grid_x", C.c_int32), ("shard_grid_y", C.c_int32), ("shard_skew", C.c_int32), ("flags", C.c_int32),
     ]
 
 

@@ -34,6 +34,6 @@ struct MathFast {
 };
 
 cudaError_t launch_march_fast(const MarchParams &p, int grid, cudaStream_t s) { return launch_march_impl<MathFast>(p, grid, s); }
-int march_fast_ctas_per_sm(int scene) { return march_ctas_per_sm_impl<MathFast>(scene); }
+int march_fast_ctas_per_sm(int scene, int flags) { return march_ctas_per_sm_impl<MathFast>(scene, flags); }
 
 }  // namespace rmdf

@@ -33,6 +33,6 @@ struct MathParity {
 };
 
 cudaError_t launch_march_parity(const MarchParams &p, int grid, cudaStream_t s) { return launch_march_impl<MathParity>(p, grid, s); }
-int march_parity_ctas_per_sm(int scene) { return march_ctas_per_sm_impl<MathParity>(scene); }
+int march_parity_ctas_per_sm(int scene, int flags) { return march_ctas_per_sm_impl<MathParity>(scene, flags); }
 
 }  // namespace rmdf

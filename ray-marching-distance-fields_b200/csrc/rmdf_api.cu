@@ -455,7 +455,7 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     if (p->mode != RMDF_MODE_PARITY && p->mode != RMDF_MODE_FAST) return fail(RMDF_ERR_ARG, "mode %d unknown", p->mode);
     if (p->lod_policy != RMDF_LOD_QUAD && p->lod_policy != RMDF_LOD_ALWAYS_LINEAR) return fail(RMDF_ERR_ARG, "lod_policy %d unknown", p->lod_policy);
     if (p->layout != RMDF_LAYOUT_FRAME && p->layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", p->layout);
-    if (p->reserved) return fail(RMDF_ERR_ARG, "reserved field must be 0");
+    if (p->flags & ~(RMDF_FLAG_NORMAL_CENTRAL | RMDF_FLAG_CAM_ORTHO | RMDF_FLAG_RAY_TRACING_TEST)) return fail(RMDF_ERR_ARG, "unknown bits in flags: 0x%x", p->flags);
     const int k = p->resolve_log2, q = 1 << k;
     const bool sharded = p->shard_count > 1;
     if (sharded && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", p->shard_rank, p->shard_count);
@@ -548,7 +548,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     WorkList wl;
     if ((rc = build_worklist(p, &wl))) return rc;
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
-    if (p->scene == RMDF_SCENE_CORNELL_BOX && !ctx->have_cornell)
+    if ((p->scene == RMDF_SCENE_CORNELL_BOX || (p->flags & RMDF_FLAG_RAY_TRACING_TEST)) && !ctx->have_cornell)
         return fail(RMDF_ERR_STATE, "Cornell scene requested before rmdf_set_cornell");
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
 
@@ -566,7 +566,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     }
     mp.bsphere_r = (p->scene == RMDF_SCENE_MB_POWER8) ? 1.15f : (p->scene == RMDF_SCENE_MB_GENERAL) ? 1.5f : 1.0f;
     mp.lod_policy = p->lod_policy; mp.resolve_log2 = p->resolve_log2;
-    mp.out_format = p->out_format; mp.layout = p->layout;
+    mp.out_format = p->out_format; mp.layout = p->layout; mp.flags = p->flags;
     mp.rect_mode = wl.rect_mode; mp.tile_x0 = wl.tile_x0; mp.tile_y0 = wl.tile_y0;
     mp.shard_gx = wl.shard_gx; mp.shard_count = p->shard_count; mp.shard_rank = p->shard_rank; mp.shard_skew = wl.shard_skew;
     mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
@@ -581,7 +581,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.queue = ctx->d_queue;
     mp.counters = ctx->d_counters;
 
-    const int ctas_per_sm = (p->mode == RMDF_MODE_FAST) ? march_fast_ctas_per_sm(p->scene) : march_parity_ctas_per_sm(p->scene);
+    const int ctas_per_sm = (p->mode == RMDF_MODE_FAST) ? march_fast_ctas_per_sm(p->scene, p->flags) : march_parity_ctas_per_sm(p->scene, p->flags);
     const int resident_warps = ctas_per_sm * ctx->sm_count * kWarpsPerCta;
     const int bx = (wl.tile_w + kBlockDim - 1) / kBlockDim;
     const int64_t blocks32 = (int64_t)bx * ((wl.tile_h + 31) / 32) * wl.n_tiles;

@@ -24,6 +24,7 @@ struct MarchParams {
     float power;                      // animated Mandelbulb power (fragment.shd:116-119)
     float bsphere_r;                  // fragment.shd:640-649
     int   lod_policy, resolve_log2, out_format, layout;
+    int   flags;                      // RMDF_FLAG_* (0 = the reference's build)
     // work list: the whole frame (0), one tile of the reference's 8×8 grid (1), or this rank's
     // tiles of the shard grid (2): (tx + skew·ty) mod count == rank, packed by ascending (ty, tx)
     int   rect_mode;
@@ -58,8 +59,8 @@ struct JuliaParams {
 // launchers implemented in march_parity.cu / march_fast.cu / julia.cu / envmap.cu
 cudaError_t launch_march_parity(const MarchParams &p, int grid, cudaStream_t s);
 cudaError_t launch_march_fast(const MarchParams &p, int grid, cudaStream_t s);
-int         march_parity_ctas_per_sm(int scene);
-int         march_fast_ctas_per_sm(int scene);
+int         march_parity_ctas_per_sm(int scene, int flags);
+int         march_fast_ctas_per_sm(int scene, int flags);
 cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s);
 int         julia_ctas_per_sm();
 cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_dev, int np,

@@ -70,7 +70,7 @@ instance Storable RmdfParams where
         i 0 pScene >> i 4 pFbW >> i 8 pFbH >> pokeByteOff p 12 pTime
         i 16 pTileIdx >> i 20 pResolveLog2 >> i 24 pOutFormat >> i 28 pMode
         i 32 pLodPolicy >> i 36 pShardRank >> i 40 pShardCount >> i 44 pLayout
-        mapM_ (\off -> i off 0) [48, 52, 56, 60]            -- shard_grid_x/y, shard_skew (0 = 8×8 grid), reserved
+        mapM_ (\off -> i off 0) [48, 52, 56, 60]            -- shard_grid_x/y, shard_skew (0 = 8×8 grid), flags (0 = the reference's build)
 
 -- | `Left <message>` like the ExceptT String the reference threads through withShaderRenderer.
 check :: CInt -> IO (Either String ())

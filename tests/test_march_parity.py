@@ -190,6 +190,22 @@ def test_fast_mode_16spp_meets_baseline_tolerance(sr, O, R, oracle_envs):
     assert p >= 50.0
 
 
+@pytest.mark.parametrize("scene,flags", [(2, 1), (2, 2), (2, 3), (1, 1), (0, 4), (0, 6), (3, 3)])
+def test_shader_options_bit_exact(sr, O, R, oracle_envs, scene, flags):
+    """The switches that are off in the reference's build (central-difference normals, CAM_ORTHO,
+    RAY_TRACING_TEST): kernel == oracle with the same switch."""
+    _bind(sr, oracle_envs)
+    w, h = 160, 96
+    ref = O.render(scene, w, h, 7.0, envs=oracle_envs, flags=flags)
+    got = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 7.0, flags=flags)
+    assert np.array_equal(got, ref["fb"]), int((got != ref["fb"]).sum())
+    lin = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 7.0, flags=flags, out_format=R.OUT_RGBA32F)
+    assert np.array_equal(lin[..., 3] > 0.5, ref["hit"].astype(bool))
+    assert np.array_equal(lin[..., :3].view(np.uint32), ref["linear"].view(np.uint32))
+    fast = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 7.0, flags=flags, out_format=R.OUT_RGBA32F, mode=R.MODE_FAST)
+    assert np.mean((fast[..., 3] > 0.5) == ref["hit"].astype(bool)) > 0.995
+
+
 def test_error_behaviour(sr, R):
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(5, None, 64, 64, 0.0)
@@ -197,3 +213,5 @@ def test_error_behaviour(sr, R):
         sr.drawShaderTile(R.FragmentShader.FSDETestShader, 3, 100, 100, 0.0)      # tiles need /16
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 66, 64, 0.0, resolve_log2=2)
+    with pytest.raises(R.RmdfError):
+        sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0, flags=64)

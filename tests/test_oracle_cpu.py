@@ -290,3 +290,28 @@ def test_camera_matches_reference_constants(O):
     assert np.allclose(O.camera(0, 0.0)[9:], [0.0, 0.4, -2.0], atol=1e-7)
     x, y, z = cam[0:3], cam[3:6], cam[6:9]
     assert abs(np.dot(x, y)) < 1e-6 and abs(np.dot(y, z)) < 1e-6 and abs(np.linalg.norm(z) - 1) < 1e-6
+
+
+def test_ray_traced_cornell_cross_checks_the_distance_estimator(O):
+    """RAY_TRACING_TEST (fragment.shd:915-937) is the reference's own cross-check of the Cornell DE:
+    the sphere tracer's hit mask must match the ray tracer's, up to the
+    silhouette pixels where MIN_DIST = 0.001 fattens the surface."""
+    w, h = 320, 180
+    de = O.render(O.SCENE_CORNELL, w, h, 0.0)["hit"].astype(bool)
+    rt = O.render(O.SCENE_CORNELL, w, h, 0.0, flags=O.FLAG_RAY_TRACING_TEST)
+    agree = (de == rt["hit"].astype(bool)).mean()
+    assert agree > 0.985, agree
+    assert (de | ~rt["hit"].astype(bool)).mean() > 0.999          # every ray-traced hit is a sphere-traced hit
+    # hit colours are (n + 1) / 2 of axis-aligned walls: only a handful of distinct colours
+    cols = {tuple(c) for c in rt["fb"][rt["hit"].astype(bool)].reshape(-1)[:, None].view(np.uint8)[:, :3]}
+    assert 3 <= len(cols) <= 40
+
+
+def test_option_flags_change_only_what_they_say(O):
+    base = O.render(2, 96, 96, 0.0)
+    cen = O.render(2, 96, 96, 0.0, flags=O.FLAG_NORMAL_CENTRAL)
+    assert np.array_equal(base["hit"], cen["hit"])                 # normals do not move the surface
+    assert cen["counters"]["shade_de"] == base["counters"]["hits"] * 8       # 6 normal + 2 AO evaluations per hit
+    assert base["counters"]["shade_de"] == base["counters"]["hits"] * 6
+    ortho = O.render(2, 96, 96, 0.0, flags=O.FLAG_CAM_ORTHO)
+    assert ortho["hit"].mean() > base["hit"].mean()                # width-2 ortho view frames the bulb tighter
