@@ -452,8 +452,19 @@ def run_julia(args):
     stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); sr.setStream(stream.cuda_stream)
     band_h = par.julia_band_height(J_FB_H, J_SPP_LOG2, world)
     n_out = J_OUT_W * J_OUT_H // world
-    out_dev = torch.empty(n_out, dtype=torch.int32, device=dev)
-    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    shared = None
+    if world > 1 and args.gather == "peer":                     # fused gather, as for the Mandelbulb frame
+        okf = 1
+        try:
+            shared = par.SharedFrame(sr, J_OUT_W * J_OUT_H, world, rank)
+        except R.RmdfError:
+            okf = 0
+        okt = torch.tensor([okf], device=dev); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0 and shared is not None:
+            shared.close(); shared = None
+    shared_frame = shared.as_tensor() if (shared is not None and rank == 0) else None
+    out_dev = torch.empty(n_out if shared is None else 1, dtype=torch.int32, device=dev)
+    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0 and shared is None) else None
     frame_host = torch.empty(J_OUT_H * J_OUT_W, dtype=torch.int32).pin_memory() if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -463,6 +474,10 @@ def run_julia(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if shared is not None:
+            sr.juliaBandsDevice(J_FB_W, J_FB_H, False, J_TICK, J_SPP_LOG2, band_h, rank, world, shared.ptr, layout=R.LAYOUT_FRAME)
+            shared.complete()
+            return shared_frame
         sr.juliaBandsDevice(J_FB_W, J_FB_H, False, J_TICK, J_SPP_LOG2, band_h, rank, world, out_dev.data_ptr())
         return par.gather_bands(out_dev, J_OUT_W, J_OUT_H, world, rank, band_h >> J_SPP_LOG2, gather_list)
 
@@ -503,7 +518,7 @@ def run_julia(args):
         line = {"metric": "julia_8k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": J_WORKLOAD, "fb": [J_FB_W, J_FB_H], "out": [J_OUT_W, J_OUT_H], "spp": 64,
-                                                "parallelism": ("row bands of %d rows, band b -> rank b mod %d, one NCCL gather" % (band_h, world)) if world > 1 else "single GPU",
+                                                "parallelism": ("row bands of %d rows, band b -> rank b mod %d, %s" % (band_h, world, "stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if world > 1 else "single GPU",
                                                 "l2": "flushed between steps (256 MiB write)"},
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 64,
                         "d2h_bytes_per_step": J_OUT_W * J_OUT_H * 4},
@@ -515,6 +530,8 @@ def run_julia(args):
             b = julia_cpu_baseline()
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+    if shared is not None:
+        torch.cuda.synchronize(); dist.barrier(); shared.close()
     sr.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

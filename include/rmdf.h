@@ -164,11 +164,13 @@ int  rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
                        int y0, int y1, int resolve_log2, void *fb_dev);
 /* Multi-GPU decomposition of the same frame (the reference splits rows with
  * forSegmentsConcurrently, Fractal2D.hs:98): the h rows are cut into bands of band_h rows and
- * this call renders the bands b with b mod shard_count == shard_rank, packed back to back in
- * ascending b (interleaving balances the ranks: interior rows cost 40 iterations, exterior
- * few).  h/band_h must be a multiple of shard_count, band_h of 1<<resolve_log2. */
+ * this call renders the bands b with b mod shard_count == shard_rank (interleaving balances the
+ * ranks: interior rows cost 40 iterations, exterior few).  layout = RMDF_LAYOUT_PACKED_TILES:
+ * this rank's bands back to back in ascending b; RMDF_LAYOUT_FRAME: each band at its place in the
+ * whole (resolved) frame, e.g. a shared frame buffer on another GPU (rmdf_shared_open).
+ * h/band_h must be a multiple of shard_count, band_h of 1<<resolve_log2. */
 int  rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int resolve_log2,
-                             int band_h, int shard_rank, int shard_count, void *fb_dev);
+                             int band_h, int shard_rank, int shard_count, int layout, void *fb_dev);
 
 /* ---- frame-buffer helpers: FrameBuffer.hs -------------------------------------- */
 /* glGenerateMipmap chain (FrameBuffer.hs:153-154): level `levels` of a w×h RGBA8

@@ -93,7 +93,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_render_device.argtypes = [vp, PP, vp]
     L.rmdf_julia.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_julia_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp]
-    L.rmdf_julia_bands_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.rmdf_julia_bands_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_mip_resolve_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.rmdf_counters_reset.argtypes = [vp]

@@ -106,7 +106,8 @@ julia_kernel(const JuliaParams P)
             __syncwarp();
         }
         const int ow = bw >> k, oh = bh >> k;
-        const long long o0 = ((long long)band_k * (P.band_h >> k) + ((by * P.item_h) >> k)) * P.out_stride + (X0 >> k);
+        // packed: this rank's bands back to back; frame: every band at its place in the whole frame
+        const long long o0 = ((long long)(P.frame_layout ? band : band_k) * (P.band_h >> k) + ((by * P.item_h) >> k)) * P.out_stride + (X0 >> k);
         const bool vec_ok = ((ow & 3) == 0) && ((P.out_stride & 3) == 0) && ((o0 & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
         if (vec_ok) {

@@ -699,12 +699,14 @@ extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double
 }
 
 extern "C" int rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int resolve_log2,
-                                       int band_h, int shard_rank, int shard_count, void *fb_dev)
+                                       int band_h, int shard_rank, int shard_count, int layout, void *fb_dev)
 {
     int rc = use(ctx); if (rc) return rc;
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    if (layout != RMDF_LAYOUT_FRAME && layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", layout);
     JuliaParams jp;
     if ((rc = julia_params(ctx, w, h, smooth, tick, 0, h, resolve_log2, band_h, shard_rank, shard_count, &jp))) return rc;
+    jp.frame_layout = (layout == RMDF_LAYOUT_FRAME) ? 1 : 0;
     return julia_launch(ctx, jp, fb_dev);
 }
 

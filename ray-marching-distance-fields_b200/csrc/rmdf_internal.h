@@ -47,6 +47,7 @@ struct MarchParams {
 
 struct JuliaParams {
     int   w, h, y0, y1, smooth, resolve_log2;
+    int   frame_layout;                       // 1: bands land at their frame position (shared frame buffer)
     int   band_h, shard_rank, shard_count;   // rows [y0,y1) cut into bands of band_h rows; this rank renders bands b ≡ rank (mod count)
     float julia_r, julia_i, fw, fh, ratio, xshift;
     int   item_h, blocks_x, blocks_y, n_items;

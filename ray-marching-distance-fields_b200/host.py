@@ -367,9 +367,10 @@ class ShaderRenderer:
         y0, y1 = rows
         check(self._lib.rmdf_julia_device(self._h, w, h, int(bool(smooth)), C.c_double(tick), y0, y1, resolve_log2, C.c_void_p(dev_ptr)))
 
-    def juliaBandsDevice(self, w, h, smooth, tick, resolve_log2, band_h, shard_rank, shard_count, dev_ptr: int) -> None:
+    def juliaBandsDevice(self, w, h, smooth, tick, resolve_log2, band_h, shard_rank, shard_count, dev_ptr: int,
+                         layout=_capi.LAYOUT_PACKED_TILES) -> None:
         check(self._lib.rmdf_julia_bands_device(self._h, w, h, int(bool(smooth)), C.c_double(tick), resolve_log2, band_h,
-                                                shard_rank, shard_count, C.c_void_p(dev_ptr)))
+                                                shard_rank, shard_count, layout, C.c_void_p(dev_ptr)))
 
     # -- multi-GPU shared frame buffer ------------------------------------------------------
     def sharedAlloc(self, nbytes: int):

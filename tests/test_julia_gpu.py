@@ -57,6 +57,12 @@ def test_julia_bands_partition_the_frame(sr, O, count):
         packed.append(out.cpu().numpy().view(np.uint32))
     got = par.assemble_bands_numpy(packed, w >> k, h >> k, count, band_h >> k)
     assert np.array_equal(got, want)
+    # frame layout: every rank writes its bands in place into one shared-size buffer
+    frame = torch.zeros((h >> k) * (w >> k), dtype=torch.int32, device="cuda")
+    for r in range(count):
+        sr.juliaBandsDevice(w, h, False, 7.0, k, band_h, r, count, frame.data_ptr(), layout=0)      # RMDF_LAYOUT_FRAME
+    sr.sync()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32).reshape(h >> k, w >> k), want)
 
 
 def test_julia_errors(sr, R):
