@@ -421,12 +421,17 @@ extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
         const float dot00 = rg_dot(e0, e0), dot01 = rg_dot(e0, e1), dot11 = rg_dot(e1, e1);
         const float inv_denom = 1.0f / (dot00 * dot11 - dot01 * dot01);
         const float len12 = rg_dot(ab12, ab12);
-        tab[i * 6 + 0] = make_float4(v0.x, v0.y, v0.z, dot00);
-        tab[i * 6 + 1] = make_float4(v1.x, v1.y, v1.z, dot01);
-        tab[i * 6 + 2] = make_float4(v2.x, v2.y, v2.z, dot11);
-        tab[i * 6 + 3] = make_float4(e0.x, e0.y, e0.z, inv_denom);
-        tab[i * 6 + 4] = make_float4(e1.x, e1.y, e1.z, len12);
-        tab[i * 6 + 5] = make_float4(ab12.x, ab12.y, ab12.z, 0.0f);
+        float4 *r = tab + i * kCornellStride;
+        r[0] = make_float4(v0.x, v0.y, v0.z, dot00);
+        r[1] = make_float4(v1.x, v1.y, v1.z, dot01);
+        r[2] = make_float4(v2.x, v2.y, v2.z, dot11);
+        r[3] = make_float4(e0.x, e0.y, e0.z, inv_denom);
+        r[4] = make_float4(e1.x, e1.y, e1.z, len12);
+        r[5] = make_float4(ab12.x, ab12.y, ab12.z, 0.0f);
+        // bounding sphere around the centroid, for exact culling in de_cornell_box (never enters a result)
+        const rg_vec3 c = rg_v3((v0.x + v1.x + v2.x) / 3.0f, (v0.y + v1.y + v2.y) / 3.0f, (v0.z + v1.z + v2.z) / 3.0f);
+        const float rad = fmaxf(rg_length(rg_sub(v0, c)), fmaxf(rg_length(rg_sub(v1, c)), rg_length(rg_sub(v2, c))));
+        r[6] = make_float4(c.x, c.y, c.z, rad * 1.0001f + 1.0e-5f);
     }
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
