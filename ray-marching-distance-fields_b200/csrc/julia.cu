@@ -57,7 +57,10 @@ julia_kernel(const JuliaParams P)
         // x depends on the column only (Fractal2D.hs:82): four columns per lane and block
         float xs[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) xs[c] = ((float)(X0 + c * 8 + mx) / P.fw) * 2.9f * P.ratio - P.xshift;
+        for (int c = 0; c < 4; c++) {
+            xs[c] = ((float)(X0 + c * 8 + mx) / P.fw) * 2.9f * P.ratio - P.xshift;
+            asm volatile("" : "+f"(xs[c]));          // keep the value: without this ptxas re-does the IEEE division per sample
+        }
 
 #pragma unroll 1
         for (int trow = 0; trow < (P.item_h >> 2); trow++) {
@@ -71,20 +74,30 @@ julia_kernel(const JuliaParams P)
                 if (c * 8 >= bw) break;                                             // warp-uniform
                 if (lx < bw && ly < bh) {
                     float zr = xs[c], zi = y;
-                    int iter = 0;
-                    for (;;) {                                                       // go, :85-90
-                        const float zr2 = zr * zr, zi2 = zi * zi;
-                        if (iter == 40 || (zr2 + zi2) > 4.0f * 4.0f) break;
-                        const float nr = (zr2 - zi2) + P.julia_r;
-                        const float ni = (zr * zi + zi * zr) + P.julia_i;
-                        if (nr == zr && ni == zi) { iter = 40; break; }              // 1-cycle detection
-                        zr = nr; zi = ni;
-                        iter++;
+                    float zr2 = zr * zr, zi2 = zi * zi;
+                    int iter = 40;
+                    // go, Fractal2D.hs:85-90, five blocks of eight iterations.  The reference's
+                    // 1-cycle test (newZ == z ⇒ maxIter) is only a shortcut: a repeating orbit never
+                    // escapes, so it ends at maxIter with the same z either way.  Testing once per block
+                    // for z == z(block start) catches every cycle whose period divides 8 — same result
+                    // (maxIter), one compare pair per eight iterations instead of per iteration.
+#pragma unroll 1
+                    for (int blk = 0; blk < 5; blk++) {
+                        const float sr0 = zr, si0 = zi;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            if ((zr2 + zi2) > 4.0f * 4.0f) { iter = blk * 8 + u; blk = 5; break; }
+                            const float nr = (zr2 - zi2) + P.julia_r;
+                            const float ni = (zr * zi + zi * zr) + P.julia_i;
+                            zr = nr; zi = ni;
+                            zr2 = zr * zr; zi2 = zi * zi;
+                        }
+                        if (blk < 5 && zr == sr0 && zi == si0) break;                // periodic: interior
                     }
                     iters += (unsigned)iter;
                     uint32_t word;
                     if (P.smooth && iter != 40) {
-                        const float v = (float)iter - rg_log(rg_log(zr * zr + zi * zi)) / log_2;
+                        const float v = (float)iter - rg_log(rg_log(zr2 + zi2)) / log_2;
                         const float ic = v > 0.0f ? v : 0.0f;
                         word = ((uint32_t)(int)truncf(ic / 40.0f * 255.0f)) << 8;
                     } else {
