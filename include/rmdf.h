@@ -144,6 +144,11 @@ typedef struct {
     int32_t shard_grid_y;   /*   grid (e.g. 32×16, skew 2) balances the ranks better: the Mandelbulb's */
     int32_t shard_skew;     /*   cost is concentrated mid-frame.  shard_grid_x % shard_count == 0.    */
     int32_t flags;          /* RMDF_FLAG_*; 0 = the shader exactly as the reference builds it */
+    int32_t row_begin;      /* render only frame-buffer rows [row_begin, row_end) of the selected work   */
+    int32_t row_end;        /*   (0,0 = all).  Lets a host pipeline a frame in horizontal stripes, e.g. copy */
+                            /*   stripe i to the CPU while stripe i+1 is marched (measured on config 4: four  */
+                            /*   stripes cost as much in launch tails as the overlap saves).  Multiples of 2<<resolve_log2 */
+                            /*   (of the shard tile height when sharded); RMDF_LAYOUT_FRAME only.              */
 } rmdf_params;
 
 /* Number of 32-bit words (RGBA8) or float4 (RGBA32F) the call will write, and the

@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("scene", C.c_int32), ("fb_w", C.c_int32), ("fb_h", C.c_int32), ("time", C.c_float),
         ("tile_idx", C.c_int32), ("resolve_log2", C.c_int32), ("out_format", C.c_int32), ("mode", C.c_int32),
         ("lod_policy", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("layout", C.c_int32),
-        ("shard_grid_x", C.c_int32), ("shard_grid_y", C.c_int32), ("shard_skew", C.c_int32), ("flags", C.c_int32),
+        ("shard_grid_x", C.c_int32), ("shard_grid_y", C.c_int32), ("shard_skew", C.c_int32), ("flags", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
     ]
 
 

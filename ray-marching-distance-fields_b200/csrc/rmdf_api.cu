@@ -443,7 +443,7 @@ extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
 // ---- frame rendering ------------------------------------------------------------------
 struct WorkList {
     int rect_mode;                    // 0 frame, 1 one tile, 2 shard
-    int tile_x0, tile_y0, shard_gx, shard_skew;
+    int tile_x0, tile_y0, shard_gx, shard_skew, shard_ty0;
     int n_tiles, tile_w, tile_h;
     int64_t out_pixels;
     int out_stride;
@@ -466,12 +466,24 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     if (sharded && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", p->shard_rank, p->shard_count);
     if (sharded && p->tile_idx >= 0) return fail(RMDF_ERR_ARG, "tile_idx and shard_count > 1 are mutually exclusive");
     memset(wl, 0, sizeof *wl);
+    const bool striped = p->row_begin != 0 || p->row_end != 0;
+    if (striped) {
+        if (p->row_begin < 0 || p->row_end > p->fb_h || p->row_begin >= p->row_end) return fail(RMDF_ERR_ARG, "rows [%d,%d) outside [0,%d)", p->row_begin, p->row_end, p->fb_h);
+        if (p->layout != RMDF_LAYOUT_FRAME) return fail(RMDF_ERR_ARG, "a row range needs RMDF_LAYOUT_FRAME");
+        if (p->tile_idx >= 0) return fail(RMDF_ERR_ARG, "tile_idx and a row range are mutually exclusive");
+    }
     if (p->tile_idx < 0 && !sharded) {
         if ((p->fb_w % q) || (p->fb_h % q)) return fail(RMDF_ERR_ARG, "frame %dx%d is not a multiple of the %dx%d resolve footprint", p->fb_w, p->fb_h, q, q);
         if (p->layout != RMDF_LAYOUT_FRAME) return fail(RMDF_ERR_ARG, "packed layout needs tile_idx >= 0 or shard_count > 1");
-        wl->rect_mode = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
         wl->out_stride = p->fb_w >> k;
         wl->out_pixels = (int64_t)(p->fb_w >> k) * (p->fb_h >> k);
+        if (striped) {                                    // a stripe is one full-width rectangle
+            if ((p->row_begin % (2 * q)) || (p->row_end % (2 * q))) return fail(RMDF_ERR_ARG, "row range must be a multiple of %d rows", 2 * q);
+            wl->rect_mode = 1; wl->n_tiles = 1;
+            wl->tile_x0 = 0; wl->tile_y0 = p->row_begin; wl->tile_w = p->fb_w; wl->tile_h = p->row_end - p->row_begin;
+            return RMDF_OK;
+        }
+        wl->rect_mode = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
         return RMDF_OK;
     }
     // Tile edges must fall on even pixel boundaries so that no 2×2 fragment quad straddles two tiles.
@@ -489,8 +501,13 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     wl->tile_w = p->fb_w / gx; wl->tile_h = p->fb_h / gy;
     if ((wl->tile_w % q) || (wl->tile_h % q)) return fail(RMDF_ERR_ARG, "tile %dx%d is not a multiple of the %dx%d resolve footprint", wl->tile_w, wl->tile_h, q, q);
     if (sharded) {
-        wl->rect_mode = 2; wl->shard_gx = gx;
-        wl->n_tiles = gy * (gx / p->shard_count);
+        int ty0 = 0, ty1 = gy;
+        if (striped) {
+            if ((p->row_begin % wl->tile_h) || (p->row_end % wl->tile_h)) return fail(RMDF_ERR_ARG, "row range must be a multiple of the shard tile height %d", wl->tile_h);
+            ty0 = p->row_begin / wl->tile_h; ty1 = p->row_end / wl->tile_h;
+        }
+        wl->rect_mode = 2; wl->shard_gx = gx; wl->shard_ty0 = ty0;
+        wl->n_tiles = (ty1 - ty0) * (gx / p->shard_count);
     } else {
         const int t = p->tile_idx % 64;                   // idx `mod` nTiles, :186-188
         wl->rect_mode = 1; wl->n_tiles = 1;
@@ -574,6 +591,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.out_format = p->out_format; mp.layout = p->layout; mp.flags = p->flags;
     mp.rect_mode = wl.rect_mode; mp.tile_x0 = wl.tile_x0; mp.tile_y0 = wl.tile_y0;
     mp.shard_gx = wl.shard_gx; mp.shard_count = p->shard_count; mp.shard_rank = p->shard_rank; mp.shard_skew = wl.shard_skew;
+    mp.shard_ty0 = wl.shard_ty0;
     mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
     mp.out_stride = wl.out_stride;
     for (int s = 0; s < RMDF_ENV_SLOTS; s++) {

@@ -30,7 +30,7 @@ struct MarchParams {
     // tiles of the shard grid (2): (tx + skew·ty) mod count == rank, packed by ascending (ty, tx)
     int   rect_mode;
     int   tile_x0, tile_y0;           // rect_mode 1: origin of the tile
-    int   shard_gx, shard_count, shard_rank, shard_skew;
+    int   shard_gx, shard_count, shard_rank, shard_skew, shard_ty0;   // shard_ty0: first tile row of a stripe
     int   tile_w, tile_h;             // level-0 size of one tile
     int   item_h;                     // rows per work item: 4, 8, 16 or 32
     int   blocks_x, blocks_y;         // 32×item_h blocks per rect

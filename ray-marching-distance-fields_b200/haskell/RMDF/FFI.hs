@@ -54,7 +54,7 @@ foreign import ccall safe "rmdf_cornell_box_vertices" c_cornell :: Ptr CFloat ->
 foreign import ccall safe "rmdf_set_cornell"       c_set_cornell :: RmdfCtx -> Ptr CFloat -> CInt -> IO CInt
 foreign import ccall safe "rmdf_julia"             c_julia      :: RmdfCtx -> CInt -> CInt -> CInt -> CDouble -> CInt -> CInt -> CInt -> Ptr Word32 -> IO CInt
 
--- | rmdf_params (include/rmdf.h): sixteen 32-bit fields.
+-- | rmdf_params (include/rmdf.h): eighteen 32-bit fields.
 data RmdfParams = RmdfParams
     { pScene, pFbW, pFbH :: !Int32
     , pTime              :: !Float
@@ -62,7 +62,7 @@ data RmdfParams = RmdfParams
     }
 
 instance Storable RmdfParams where
-    sizeOf    _ = 64
+    sizeOf    _ = 72
     alignment _ = 4
     peek _      = error "RmdfParams: write-only"
     poke p RmdfParams { .. } = do
@@ -70,7 +70,7 @@ instance Storable RmdfParams where
         i 0 pScene >> i 4 pFbW >> i 8 pFbH >> pokeByteOff p 12 pTime
         i 16 pTileIdx >> i 20 pResolveLog2 >> i 24 pOutFormat >> i 28 pMode
         i 32 pLodPolicy >> i 36 pShardRank >> i 40 pShardCount >> i 44 pLayout
-        mapM_ (\off -> i off 0) [48, 52, 56, 60]            -- shard_grid_x/y, shard_skew (0 = 8×8 grid), flags (0 = the reference's build)
+        mapM_ (\off -> i off 0) [48, 52, 56, 60, 64, 68]            -- shard_grid_x/y, shard_skew (0 = 8×8 grid), flags (0 = the reference's build), row_begin/row_end (0,0 = all rows)
 
 -- | `Left <message>` like the ExceptT String the reference threads through withShaderRenderer.
 check :: CInt -> IO (Either String ())

@@ -308,7 +308,7 @@ class ShaderRenderer:
     # -- ShaderRendering.hs:151-196 ----------------------------------------------------
     def makeParams(self, shdEnum, tileIdx: Optional[int], w: int, h: int, time: float, *, resolve_log2=0,
                    out_format=_capi.OUT_RGBA8, mode=_capi.MODE_PARITY, lod_policy=_capi.LOD_QUAD,
-                   shard_rank=0, shard_count=1, layout=_capi.LAYOUT_FRAME, shard_grid=(0, 0), shard_skew=0, flags=0) -> Params:
+                   shard_rank=0, shard_count=1, layout=_capi.LAYOUT_FRAME, shard_grid=(0, 0), shard_skew=0, flags=0, rows=(0, 0)) -> Params:
         p = Params()
         p.scene = int(shdEnum); p.fb_w = int(w); p.fb_h = int(h)
         p.time = float(np.float32(time))                 # realToFrac :: Double -> Float (:171)
@@ -316,6 +316,7 @@ class ShaderRenderer:
         p.resolve_log2 = resolve_log2; p.out_format = out_format; p.mode = mode; p.lod_policy = lod_policy
         p.shard_rank = shard_rank; p.shard_count = shard_count; p.layout = layout
         p.shard_grid_x, p.shard_grid_y = shard_grid; p.shard_skew = shard_skew; p.flags = flags
+        p.row_begin, p.row_end = rows
         return p
 
     def outputPixels(self, p: Params):

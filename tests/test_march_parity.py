@@ -161,6 +161,36 @@ def test_peer_frame_buffer_two_gpus(R, oracle_envs):
     assert np.array_equal(got, want)
 
 
+def test_row_ranges_compose_and_striped_host_path(sr, O, R, oracle_envs):
+    """rows=(y0, y1): horizontal stripes of the frame (and of a rank's shard) land in place, so a
+    host can pipeline a frame (copy stripe i while stripe i+1 is marched)."""
+    _bind(sr, oracle_envs)
+    w, h, k = 512, 1536, 1
+    full = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+    acc = np.zeros_like(full)
+    for y0, y1 in ((0, 512), (512, 516), (516, 1536)):
+        acc |= sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k, rows=(y0, y1))
+    assert np.array_equal(acc, full)
+    # sharded stripes: two ranks × two stripes
+    acc = np.zeros_like(full)
+    for r in range(2):
+        for y0, y1 in ((0, 768), (768, 1536)):
+            acc |= sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k, rows=(y0, y1),
+                                     shard_rank=r, shard_count=2, shard_grid=(8, 16), shard_skew=1)
+    assert np.array_equal(acc, full)
+    # a larger frame through the host-pointer call
+    w, h = 2048, 1024
+    want = O.render(1, w, h, 0.0, envs=oracle_envs)["fb"]
+    got = sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, w, h, 0.0)
+    assert np.array_equal(got, want)
+    c = sr.counters()
+    assert c["last_kernel_ms"] > 0
+    with pytest.raises(R.RmdfError):
+        sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0, rows=(2, 64), resolve_log2=1)    # not a multiple of 4
+    with pytest.raises(R.RmdfError):
+        sr.drawShaderTile(R.FragmentShader.FSDETestShader, 3, 64, 64, 0.0, rows=(0, 32))
+
+
 def test_fast_mode_within_tolerance(sr, O, R, oracle_envs):
     """Fast mode (FMA contraction, MUFU, HW filtering) vs the oracle at BASELINE's tolerance."""
     _bind(sr, oracle_envs)
