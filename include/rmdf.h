@@ -99,6 +99,10 @@ int  rmdf_envmap_convolve(rmdf_ctx *ctx, const float *rgb, int w, int h,
 /* Same, with source and destination already in device memory on ctx's device. */
 int  rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
                                  const float *powers, int np, void *out_dev);
+/* Multi-GPU decomposition of the sweep: only destination rows [row_begin, row_end) are
+ * computed and written (in place inside the full np·w·h·3 output); every rank reads the whole source. */
+int  rmdf_envmap_convolve_rows_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
+                                      const float *powers, int np, int row_begin, int row_end, void *out_dev);
 /* The RGBE quantisation a cache file applies (JP.saveRadianceImage then loadHDRImage,
  * ShaderRendering.hs:84,147): in-place on npix RGB triples (host memory). */
 int  rmdf_rgbe_roundtrip(float *rgb, int64_t npix);

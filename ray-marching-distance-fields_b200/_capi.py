@@ -21,7 +21,7 @@ FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST = 1, 2, 4
 
 EXPORTS = [
     "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
-    "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device",
+    "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device", "rmdf_envmap_convolve_rows_device",
     "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
     "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak",
@@ -81,6 +81,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_envmap_resize.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_envmap_convolve.argtypes = [vp, vp, C.c_int, C.c_int, fp, C.c_int, vp]
     L.rmdf_envmap_convolve_device.argtypes = [vp, vp, C.c_int, C.c_int, fp, C.c_int, vp]
+    L.rmdf_envmap_convolve_rows_device.argtypes = [vp, vp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_rgbe_roundtrip.argtypes = [vp, C.c_int64]
     L.rmdf_envmap_bind.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
     L.rmdf_envmap_bind_cube.argtypes = [vp, C.c_int, vp, C.c_int]

@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(CV_THREADS)
 convolve_kernel(const float *__restrict__ src, int w, int h, const float *__restrict__ tab,
                 const float *__restrict__ cth, const float *__restrict__ sth,
                 float p0, float p1, float p2, float p3, int np, int rows_per_split,
-                float *__restrict__ partial)
+                int dst_y0, int dst_y1, float *__restrict__ partial)
 {
     extern __shared__ float smem[];
     float *s_tab = smem;                                  // [w][CV_DX]  (transposed slice)
     float4 *s_row = reinterpret_cast<float4 *>(smem + (size_t)w * CV_DX);   // [2][w]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int dstx = blockIdx.x * CV_DX + tx, dsty = blockIdx.y * CV_DY + ty;
-    const bool valid = dstx < w && dsty < h;
+    const int dstx = blockIdx.x * CV_DX + tx, dsty = dst_y0 + blockIdx.y * CV_DY + ty;       // destination rows [dst_y0, dst_y1)
+    const bool valid = dstx < w && dsty < dst_y1;
 
     for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) {
         const int sx = i / CV_DX, dx = blockIdx.x * CV_DX + (i % CV_DX);
@@ -106,10 +106,10 @@ convolve_kernel(const float *__restrict__ src, int w, int h, const float *__rest
 }
 
 // out[p][y][x][c] = Σ_splits acc / Σ_splits n   ("divide sum by number of hemisphere samples", :231-232)
-__global__ void convolve_finish_kernel(const float *__restrict__ partial, int npix, int splits, int np, float *__restrict__ out)
+__global__ void convolve_finish_kernel(const float *__restrict__ partial, int npix, int splits, int np, int i0, int i1, float *__restrict__ out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
     float acc[12], n = 0.0f;
     for (int k = 0; k < 12; k++) acc[k] = 0.0f;
     for (int s = 0; s < splits; s++) {
@@ -138,7 +138,7 @@ static void convolve_tables(int w, int h, float *tab, float *cth, float *sth)
 }
 
 cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_host, int np,
-                            float *out_dev, cudaStream_t s)
+                            float *out_dev, int dst_y0, int dst_y1, cudaStream_t s)
 {
     cudaError_t e;
     const size_t ntab = (size_t)w * w;
@@ -154,7 +154,7 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // host table is freed below
     free(host);
     const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
-    const dim3 grid((w + CV_DX - 1) / CV_DX, (h + CV_DY - 1) / CV_DY, splits);
+    const dim3 grid((w + CV_DX - 1) / CV_DX, (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY, splits);
     for (int first = 0; first < np && e == cudaSuccess; first += 4) {
         const int cnt = (np - first < 4) ? np - first : 4;
         float p[4] = { 0, 0, 0, 0 };
@@ -163,15 +163,16 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
         if (chain) {
             cudaFuncSetAttribute(convolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             convolve_kernel<true><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                 p[0], p[1], p[2], p[3], cnt, rows_per_split, d_partial);
+                                                                 p[0], p[1], p[2], p[3], cnt, rows_per_split, dst_y0, dst_y1, d_partial);
         } else {
             cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             convolve_kernel<false><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                  p[0], p[1], p[2], p[3], cnt, rows_per_split, d_partial);
+                                                                  p[0], p[1], p[2], p[3], cnt, rows_per_split, dst_y0, dst_y1, d_partial);
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
-        convolve_finish_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(d_partial, (int)npix, splits, cnt, out_dev + (size_t)first * npix * 3);
+        const int i0 = dst_y0 * w, i1 = dst_y1 * w;
+        convolve_finish_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, s>>>(d_partial, (int)npix, splits, cnt, i0, i1, out_dev + (size_t)first * npix * 3);
         e = cudaGetLastError();
     }
     cudaFreeAsync(d_tab, s);

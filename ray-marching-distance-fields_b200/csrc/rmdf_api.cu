@@ -190,19 +190,25 @@ static int convolve_check(const void *rgb, int w, int h, const float *powers, in
     if (np < 1 || np > 64) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: np = %d out of range [1,64]", np);
     return RMDF_OK;
 }
-extern "C" int rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
-                                           const float *powers, int np, void *out_dev)
+extern "C" int rmdf_envmap_convolve_rows_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
+                                                const float *powers, int np, int row_begin, int row_end, void *out_dev)
 {
     int rc = use(ctx); if (rc) return rc;
     if ((rc = convolve_check(rgb_dev, w, h, powers, np, out_dev))) return rc;
+    if (row_begin < 0 || row_end > h || row_begin >= row_end) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: rows [%d,%d) outside [0,%d)", row_begin, row_end, h);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = launch_convolve((const float *)rgb_dev, w, h, powers, np, (float *)out_dev, ctx->stream);
+    cudaError_t e = launch_convolve((const float *)rgb_dev, w, h, powers, np, (float *)out_dev, row_begin, row_end, ctx->stream);
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_convolve: %s", cudaGetErrorString(e));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     ctx->launches += 2 * (uint64_t)((np + 3) / 4);
     return RMDF_OK;
+}
+extern "C" int rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
+                                           const float *powers, int np, void *out_dev)
+{
+    return rmdf_envmap_convolve_rows_device(ctx, rgb_dev, w, h, powers, np, 0, h, out_dev);
 }
 extern "C" int rmdf_envmap_convolve(rmdf_ctx *ctx, const float *rgb, int w, int h,
                                     const float *powers, int np, float *out)

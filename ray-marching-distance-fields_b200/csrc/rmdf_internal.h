@@ -65,8 +65,8 @@ int         march_parity_ctas_per_sm(int scene, int flags);
 int         march_fast_ctas_per_sm(int scene, int flags);
 cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s);
 int         julia_ctas_per_sm();
-cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_dev, int np,
-                            float *out_dev, cudaStream_t s);
+cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_host, int np,
+                            float *out_dev, int dst_y0, int dst_y1, cudaStream_t s);
 cudaError_t launch_resize(const float *src_dev, int w, int h, int dstw, int dsth, float *out_dev, cudaStream_t s);
 cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int face_w, float *faces_dev, cudaStream_t s);
 cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s);

@@ -56,6 +56,25 @@ def test_convolve_device_pointers(sr, O, R, uffizi):
     assert sr.counters()["last_kernel_ms"] > 0.0
 
 
+def test_convolve_row_ranges_compose(sr, O, R, uffizi):
+    """the sweep shards by destination rows; every rank reads the whole source.  Row
+    ranges computed separately equal the one-pass result bit for bit (same per-pixel summation order)."""
+    import torch
+    small = O.resize(uffizi, 96)                                  # 96×48
+    h, w = small.shape[:2]
+    src = torch.from_numpy(small).cuda()
+    pw = (C.c_float * 4)(1.0, 8.0, 64.0, 512.0)
+    whole = torch.zeros((4, h, w, 3), dtype=torch.float32, device="cuda")
+    R._capi.check(sr._lib.rmdf_envmap_convolve_device(sr.handle, src.data_ptr(), w, h, pw, 4, whole.data_ptr()))
+    parts = torch.zeros_like(whole)
+    for y0, y1 in ((0, 7), (7, 24), (24, 48)):                    # ragged against the 8-row CTA tile
+        R._capi.check(sr._lib.rmdf_envmap_convolve_rows_device(sr.handle, src.data_ptr(), w, h, pw, 4, y0, y1, parts.data_ptr()))
+    sr.sync()
+    assert torch.equal(parts, whole)
+    with pytest.raises(R.RmdfError):
+        R._capi.check(sr._lib.rmdf_envmap_convolve_rows_device(sr.handle, src.data_ptr(), w, h, pw, 4, 10, 10, parts.data_ptr()))
+
+
 def test_counters_accumulate_and_reset(sr, R):
     sr.resetCounters()
     sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0)

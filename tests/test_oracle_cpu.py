@@ -315,3 +315,98 @@ def test_option_flags_change_only_what_they_say(O):
     assert base["counters"]["shade_de"] == base["counters"]["hits"] * 6
     ortho = O.render(2, 96, 96, 0.0, flags=O.FLAG_CAM_ORTHO)
     assert ortho["hit"].mean() > base["hit"].mean()                # width-2 ortho view frames the bulb tighter
+
+
+# ------------------------------------------------------------------ whole-pipeline second restatement
+def _np_render_mandelbulb_white(O, w, h, t):
+    """fragment.shd main() for the POWER8 Mandelbulb with all env maps = 1.0, written a second time,
+    vectorised in numpy float32 straight from the shader text (camera :884-902, lookat :829-838,
+    generate_ray :840-871, ray_sphere :595-616, ray_march :618-676, normal :463-470, distance_ao
+    :542-562, fresnel :694-719, shading :799-810, gamma :956-960).  Uses only IEEE float32 numpy
+    arithmetic plus the deterministic built-ins (O.glsl) for sin/cos/tan/log/pow."""
+    g1 = lambda fn, x, y=None: O.glsl(fn, np.asarray([x], f32), None if y is None else np.asarray([y], f32))[0]
+    T = f32(t)
+    cp = np.array([g1("sin", T / f32(3)), g1("cos", T / f32(4)), g1("cos", T / f32(3))], f32)
+    dot = lambda a, b: (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+    inv = lambda d: (f32(1) / np.sqrt(d)).astype(f32)
+    norm = lambda v: (v * inv(dot(v, v))[..., None]).astype(f32)
+    eye = (norm(cp) * f32(2.414213562373095)).astype(f32)
+    z = norm(eye - f32(0)); up = np.array([0, 1, 0], f32)
+    cross = lambda a, b: np.stack([a[..., 1] * b[..., 2] - b[..., 1] * a[..., 2], a[..., 2] * b[..., 0] - b[..., 2] * a[..., 0],
+                                   a[..., 0] * b[..., 1] - b[..., 0] * a[..., 1]], -1).astype(f32)
+    x = norm(cross(up, z)); y = cross(z, x)
+    py, px = np.meshgrid(np.arange(h, dtype=f32), np.arange(w, dtype=f32), indexing="ij")
+    fw, fh = f32(w), f32(h)
+    ndc_x = (px + f32(0.5)) / fw * f32(2) - f32(1); ndc_y = (py + f32(0.5)) / fh * f32(2) - f32(1)
+    fov = g1("tan", f32(45.0 * 1.5) * f32(0.017453292519943295) / f32(2))
+    v = norm(np.stack([ndc_x * fov, ndc_y * fov / (fw / fh), np.full_like(ndc_x, -1)], -1).astype(f32))
+    d = np.stack([(x[i] * v[..., 0] + y[i] * v[..., 1]) + z[i] * v[..., 2] for i in range(3)], -1).astype(f32)
+    d = d.reshape(-1, 3); n_px = len(d)
+    o = np.broadcast_to(eye, d.shape)
+    de = lambda p: _np_mandelbulb8(O, p)
+    with np.errstate(all="ignore"):
+        rs = (f32(0) - o).astype(f32)
+        tc = dot(d, rs); a = dot(rs, rs) - tc * tc; r2 = f32(1.15) * f32(1.15)
+        insph = ~(a > r2)
+        hh = np.sqrt(np.where(insph, r2 - a, 0)).astype(f32)
+        tmax = tc + hh; tt = np.maximum(f32(0), tc - hh).astype(f32)
+        alive = insph.copy(); hit = np.zeros(n_px, bool)
+        for _ in range(128):
+            if not alive.any():
+                break
+            idx = np.nonzero(alive)[0]
+            pos = (o[idx] + d[idx] * tt[idx, None]).astype(f32)
+            dist = de(pos)
+            tn = (tt[idx] + dist).astype(f32)
+            tt[idx] = tn
+            left = tn > tmax[idx]
+            close = ~left & (dist < f32(0.001))
+            hit[idx[close]] = True
+            alive[idx[left | close]] = False
+        hi = np.nonzero(hit)[0]
+        isec = (o[hi] + d[hi] * tt[hi, None]).astype(f32)
+        p0 = (isec - d[hi] * f32(0.00001)).astype(f32)
+        eps = f32(0.00001)
+        c0 = de(p0)
+        gx = c0 - de((p0 - np.array([eps, 0, 0], f32)).astype(f32))
+        gy = c0 - de((p0 - np.array([0, eps, 0], f32)).astype(f32))
+        gz = c0 - de((p0 - np.array([0, 0, eps], f32)).astype(f32))
+        n = norm(np.stack([gx, gy, gz], -1).astype(f32))
+        occ = np.zeros(len(hi), f32)
+        for wgt, dl in ((f32(0.5), f32(0.016)), (f32(0.25), f32(0.081))):
+            dd = de((isec + n * dl).astype(f32))
+            term = f32(1) - dd / dl
+            term = np.where(term < 0, f32(0), term); term = np.where(term > 1, f32(1), term)      # clamp = min(max(x,0),1)
+            occ = (occ + wgt * term).astype(f32)
+        occ = f32(1) - occ; occ = occ - f32(0.29); occ = occ * f32(3.5); occ = occ * occ
+        occ = np.where(occ < 0, f32(0), occ); ao = np.where(occ > 1, f32(1), occ).astype(f32)
+        cosi = dot(-d[hi], n); eta, kk = f32(0.4), f32(0.8)
+        tmp = (eta * eta + kk * kk) * cosi * cosi
+        rpar = (tmp - (f32(2) * eta * cosi) + f32(1)) / (tmp + (f32(2) * eta * cosi) + f32(1))
+        tf = eta * eta + kk * kk
+        rper = (tf - (f32(2) * eta * cosi) + cosi * cosi) / (tf + (f32(2) * eta * cosi) + cosi * cosi)
+        fres = ((rpar + rper) / f32(2)).astype(f32)
+        one = np.ones(len(hi), f32)
+        col = []
+        for dc, sc in ((f32(1), f32(0.8)), (f32(0.8), f32(0.8)), (f32(0.8), f32(1))):
+            t1 = one * dc * f32(0.5)
+            t2 = one * sc * f32(5) * fres * f32(0.5)
+            t3 = one * f32(0.5) * fres * f32(0.1)
+            col.append((((t1 + t2) + t3) * f32(3) * ao).astype(f32))
+        color = np.ones((n_px, 3), f32)                         # misses: texture(env_reflection, dir) = 1
+        color[hi] = np.stack(col, -1)
+    gam = O.glsl("pow", color.reshape(-1), f32(1.0) / f32(2.2)).reshape(-1, 3)
+    u8 = O.glsl("unorm8", gam.reshape(-1)).reshape(-1, 3).astype(np.uint32)
+    fb = u8[:, 0] | (u8[:, 1] << 8) | (u8[:, 2] << 16) | np.uint32(0xFF000000)
+    return fb.reshape(h, w), hit.reshape(h, w)
+
+
+@pytest.mark.parametrize("t", [0.0, 7.0])
+def test_whole_pipeline_matches_numpy_restatement(O, t):
+    """The C oracle's full per-pixel pipeline against an independent numpy restatement of the shader:
+    identical RGBA8 words and hit mask (bit for bit — both are IEEE-only and share the built-ins)."""
+    w, h = 40, 32
+    fb, hit = _np_render_mandelbulb_white(O, w, h, t)
+    ref = O.render(O.SCENE_MB_POWER8, w, h, t)
+    assert np.array_equal(hit, ref["hit"].astype(bool))
+    assert np.array_equal(fb, ref["fb"]), int((fb != ref["fb"]).sum())
