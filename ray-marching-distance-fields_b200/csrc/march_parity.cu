@@ -18,7 +18,7 @@ struct MathParity {
 #define RMDF_MARCH_NOINLINE 0
 #endif
     static constexpr bool kNoinlineMarch = RMDF_MARCH_NOINLINE;
-    static constexpr int  kMinCtas = RMDF_MIN_CTAS;
+    static constexpr int  min_ctas(int, bool) { return RMDF_MIN_CTAS; }
     static constexpr bool kNoinlineDE = RMDF_DE_NOINLINE;
     static __device__ __forceinline__ float sqrt(float x) { return rg_sqrt(x); }
     static __device__ __forceinline__ float inversesqrt(float x) { return rg_inversesqrt(x); }
