@@ -8,22 +8,72 @@
 // variant's log(log |z|²)/log 2 uses the deterministic rg_log (≤ 1 ulp from libm).
 //
 // Same work decomposition as the march kernel: persistent CTAs, one atomicAdd per
-// 32×32 block of samples, 8×4 Morton tiles per warp, RGBA8 staging in shared memory,
-// in-place mip resolve (supersampling), 128-bit stores.
+// 32×item_h block of samples, RGBA8 staging in shared memory, in-place mip resolve
+// (supersampling), 128-bit stores.  A warp covers 16×4 samples, two adjacent columns per
+// lane, and iterates both in packed FP32 (csrc/packed_f32.cuh).
+//
+// The frame of BASELINE config 5 averages 3.8 iterations per sample, so the per-sample
+// bookkeeping weighs as much as the orbit: the smooth switch is a template parameter, the
+// first block of eight iterations is peeled (its periodicity reference is the start value,
+// no copies), and the resolve works on the green byte alone (the other three are zero).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/rmdf_glsl.h"
 #include "rmdf_internal.h"
+#include "packed_f32.cuh"
 
 namespace rmdf {
 
-__device__ __forceinline__ uint32_t j_box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+// (a+b+c+d+2)>>2 per byte (the glGenerateMipmap box of oracle convention C6) for words that hold
+// only a green byte, 0x0000GG00: the sum of four cannot carry out of bits 8..17.
+__device__ __forceinline__ uint32_t j_box4_green(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
-    uint32_t lo = (a & 0x00ff00ffu) + (b & 0x00ff00ffu) + (c & 0x00ff00ffu) + (d & 0x00ff00ffu) + 0x00020002u;
-    uint32_t hi = ((a >> 8) & 0x00ff00ffu) + ((b >> 8) & 0x00ff00ffu) + ((c >> 8) & 0x00ff00ffu) + ((d >> 8) & 0x00ff00ffu) + 0x00020002u;
-    return ((lo >> 2) & 0x00ff00ffu) | (((hi >> 2) & 0x00ff00ffu) << 8);
+    return (((a + b) + (c + d) + 0x200u) >> 2) & 0xff00u;
 }
 
+// pixel word of one sample: toGreen . truncate $ fromIntegral iCnt / 40 * 255 (Fractal2D.hs:93-97); the smooth
+// variant subtracts log(log |z|²)/log 2 at the escape (fractionalIterCnt, :24-25)
+template <bool SMOOTH>
+__device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2, const uint32_t *lut)
+{
+    if (SMOOTH && iter != 40) {
+        const float v = (float)iter - rg_log(rg_log(mag2)) / log_2;
+        const float ic = v > 0.0f ? v : 0.0f;
+        return ((uint32_t)(int)truncf(ic / 40.0f * 255.0f)) << 8;
+    }
+    return lut[iter];
+}
+
+// One orbit step for both slots (go, Fractal2D.hs:85-90): the escape test comes first; `it` is the
+// iteration number recorded for a slot that escapes here.  A slot that has escaped is frozen by
+// poisoning its additive constant with NaN: its orbit is NaN from the next update on and `|z|² > 16`
+// stays false for it, so the common path costs one max + one compare for both slots.
+#define RMDF_JULIA_STEP(it)                                                                       \
+    {                                                                                             \
+        const f2 m = zr2 + zi2;                                                                   \
+        if (fmaxf(m.x, m.y) > 4.0f * 4.0f) {                                                      \
+            if (m.x > 16.0f) { it0 = (it); m0 = m.x; done |= 1u; jr.x = kNaN; }                   \
+            if (m.y > 16.0f) { it1 = (it); m1 = m.y; done |= 2u; jr.y = kNaN; }                   \
+            if (done == 3u) goto finished;                                                        \
+        }                                                                                         \
+        const f2 nr = (zr2 - zi2) + jr;                                                           \
+        const f2 p = zr * zi;                                                                     \
+        const f2 ni = (p + p) + ji;                                                               \
+        zr = nr; zi = ni;                                                                         \
+        zr2 = zr * zr; zi2 = zi * zi;                                                             \
+    }
+// The reference's 1-cycle test (newZ == z ⇒ maxIter) is only a shortcut: a repeating orbit never escapes, so it
+// ends at maxIter with the same z either way.  Testing once per block of eight iterations for
+// z == z(block start) catches every cycle whose period divides 8 — same result (maxIter), one compare pair per
+// eight iterations instead of per iteration.
+#define RMDF_JULIA_PERIODIC(sr, si)                                                               \
+    {                                                                                             \
+        if (zr.x == (sr).x && zi.x == (si).x) { done |= 1u; jr.x = kNaN; }                        \
+        if (zr.y == (sr).y && zi.y == (si).y) { done |= 2u; jr.y = kNaN; }                        \
+        if (done == 3u) goto finished;                                                            \
+    }
+
+template <bool SMOOTH>
 __global__ void __launch_bounds__(kCtaThreads, 8)
 julia_kernel(const JuliaParams P)
 {
@@ -35,10 +85,11 @@ julia_kernel(const JuliaParams P)
     // toGreen . truncate $ fromIntegral iCnt / 40 * 255  (Fractal2D.hs:93-97)
     if (threadIdx.x < 41) s_lut[threadIdx.x] = ((uint32_t)(int)truncf((float)threadIdx.x / 40.0f * 255.0f)) << 8;
     __syncthreads();
-    const int mx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
-    const int my = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+    const int mx = lane & 7, my = lane >> 3;        // a warp covers 16×4 samples: lane = 2 adjacent columns of one row
+    const float kNaN = __int_as_float(0x7fffffff);
     const int k = P.resolve_log2;
     const float log_2 = rg_log(2.0f);
+    const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
     for (;;) {
@@ -54,12 +105,14 @@ julia_kernel(const JuliaParams P)
         const int bw = min(kBlockDim, P.w - bx * kBlockDim), bh = min(P.item_h, P.band_h - by * P.item_h);
         const int X0 = bx * kBlockDim, Y0 = P.y0 + band * P.band_h + by * P.item_h;
 
-        // x depends on the column only (Fractal2D.hs:82): four columns per lane and block
-        float xs[4];
+        // x depends on the column only (Fractal2D.hs:82): the four column values of a lane are hoisted per block
+        f2 xs[2];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            xs[c] = ((float)(X0 + c * 8 + mx) / P.fw) * 2.9f * P.ratio - P.xshift;
-            asm volatile("" : "+f"(xs[c]));          // keep the value: without this ptxas re-does the IEEE division per sample
+        for (int c = 0; c < 2; c++) {
+            const int col = X0 + c * 16 + 2 * mx;
+            xs[c].x = ((float)col / P.fw) * 2.9f * P.ratio - P.xshift;
+            xs[c].y = ((float)(col + 1) / P.fw) * 2.9f * P.ratio - P.xshift;
+            asm volatile("" : "+f"(xs[c].x), "+f"(xs[c].y));   // keep the values: without this ptxas re-does the IEEE divisions per sample
         }
 
 #pragma unroll 1
@@ -67,54 +120,53 @@ julia_kernel(const JuliaParams P)
             const int ty = trow * 4;
             if (ty >= bh) break;
             const int ly = ty + my;
-            const float y = ((float)(Y0 + ly) / P.fh) * 2.9f - 1.45f;               // :81
+            const f2 ys = F2(((float)(Y0 + ly) / P.fh) * 2.9f - 1.45f);             // :81
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int lx = c * 8 + mx;
-                if (c * 8 >= bw) break;                                             // warp-uniform
-                if (lx < bw && ly < bh) {
-                    float zr = xs[c], zi = y;
-                    float zr2 = zr * zr, zi2 = zi * zi;
-                    int iter = 40;
-                    // go, Fractal2D.hs:85-90, five blocks of eight iterations.  The reference's
-                    // 1-cycle test (newZ == z ⇒ maxIter) is only a shortcut: a repeating orbit never
-                    // escapes, so it ends at maxIter with the same z either way.  Testing once per block
-                    // for z == z(block start) catches every cycle whose period divides 8 — same result
-                    // (maxIter), one compare pair per eight iterations instead of per iteration.
+            for (int c = 0; c < 2; c++) {
+                const int lx = c * 16 + 2 * mx;
+                if (c * 16 >= bw) break;                                            // warp-uniform
+                unsigned live = 0u;
+                if (ly < bh) live = (lx < bw ? 1u : 0u) | (lx + 1 < bw ? 2u : 0u);
+                uint32_t w0 = 0u, w1 = 0u;                                           // the two pixel words (toGreen, :93-94)
+                if (live) {
+                    f2 jr = F2(P.julia_r), zr = xs[c], zi = ys;
+                    if (live != 3u) { jr.y = kNaN; zr.y = kNaN; }                   // slot 1 alone cannot be live
+                    f2 zr2 = zr * zr, zi2 = zi * zi;
+                    int it0 = 40, it1 = 40;
+                    float m0 = 0.0f, m1 = 0.0f;                                      // |z|² at the escape
+                    unsigned done = live ^ 3u;
+                    // iterations 0..7: the block's start value is (xs, ys) itself
+                    RMDF_JULIA_STEP(0) RMDF_JULIA_STEP(1) RMDF_JULIA_STEP(2) RMDF_JULIA_STEP(3)
+                    RMDF_JULIA_STEP(4) RMDF_JULIA_STEP(5) RMDF_JULIA_STEP(6) RMDF_JULIA_STEP(7)
+                    RMDF_JULIA_PERIODIC(xs[c], ys)
+                    {
+                        int base = 8;
 #pragma unroll 1
-                    for (int blk = 0; blk < 5; blk++) {
-                        const float sr0 = zr, si0 = zi;
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            if ((zr2 + zi2) > 4.0f * 4.0f) { iter = blk * 8 + u; blk = 5; break; }
-                            const float nr = (zr2 - zi2) + P.julia_r;
-                            const float ni = (zr * zi + zi * zr) + P.julia_i;
-                            zr = nr; zi = ni;
-                            zr2 = zr * zr; zi2 = zi * zi;
+                        for (; base < 40; base += 8) {
+                            const f2 sr0 = zr, si0 = zi;
+                            RMDF_JULIA_STEP(base)     RMDF_JULIA_STEP(base + 1) RMDF_JULIA_STEP(base + 2) RMDF_JULIA_STEP(base + 3)
+                            RMDF_JULIA_STEP(base + 4) RMDF_JULIA_STEP(base + 5) RMDF_JULIA_STEP(base + 6) RMDF_JULIA_STEP(base + 7)
+                            RMDF_JULIA_PERIODIC(sr0, si0)
                         }
-                        if (blk < 5 && zr == sr0 && zi == si0) break;                // periodic: interior
                     }
-                    iters += (unsigned)iter;
-                    uint32_t word;
-                    if (P.smooth && iter != 40) {
-                        const float v = (float)iter - rg_log(rg_log(zr2 + zi2)) / log_2;
-                        const float ic = v > 0.0f ? v : 0.0f;
-                        word = ((uint32_t)(int)truncf(ic / 40.0f * 255.0f)) << 8;
-                    } else {
-                        word = s_lut[iter];
-                    }
-                    stage[ly * kBlockDim + lx] = word;                               // toGreen, :93-94
-                    samples++;
+                finished:
+                    w0 = julia_word<SMOOTH>(it0, m0, log_2, s_lut);
+                    iters += (unsigned)it0; samples++;
+                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, s_lut); iters += (unsigned)it1; samples++; }
                 }
+                if (live == 3u) *reinterpret_cast<uint2 *>(stage + ly * kBlockDim + lx) = make_uint2(w0, w1);
+                else if (live)  stage[ly * kBlockDim + lx] = w0;
             }
         }
         __syncwarp();
         for (int l = 1; l <= k; l++) {
             const int lw = bw >> l, lh = bh >> l, h = 1 << (l - 1);
             for (int g = lane; g < lw * lh; g += 32) {
-                const int y = g / lw, x = g - y * lw;
+                int y, x;
+                if (bw == kBlockDim) { y = g >> (5 - l); x = g & (lw - 1); }        // full-width block: no division
+                else                 { y = g / lw; x = g - y * lw; }
                 uint32_t *p = stage + ((y << l) * kBlockDim + (x << l));
-                p[0] = j_box4(p[0], p[h], p[h * kBlockDim], p[h * kBlockDim + h]);
+                p[0] = j_box4_green(p[0], p[h], p[h * kBlockDim], p[h * kBlockDim + h]);
             }
             __syncwarp();
         }
@@ -151,17 +203,21 @@ julia_kernel(const JuliaParams P)
         atomicAdd(P.counters + C_ITERS, (unsigned long long)iters);
     }
 }
+#undef RMDF_JULIA_STEP
+#undef RMDF_JULIA_PERIODIC
 
 cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s)
 {
-    julia_kernel<<<grid, kCtaThreads, 0, s>>>(p);
+    if (p.smooth) julia_kernel<true><<<grid, kCtaThreads, 0, s>>>(p);
+    else          julia_kernel<false><<<grid, kCtaThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 int julia_ctas_per_sm()
 {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, julia_kernel, kCtaThreads, 0) != cudaSuccess || n < 1) n = 1;
-    return n;
+    int n = 0, m = 0;                          // one grid size for both variants: the smaller occupancy
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, julia_kernel<false>, kCtaThreads, 0) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, julia_kernel<true>, kCtaThreads, 0) != cudaSuccess || m < 1) m = 1;
+    return n < m ? n : m;
 }
 
 }  // namespace rmdf
