@@ -34,6 +34,26 @@ from pathlib import Path
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at the first
+# collective), so file descriptor 1 is pointed at stderr for everything else and the result line goes to the
+# original stdout.
+# original stdout (done in main(), not on import: profiles/*.py import helpers from this file).
+_RESULT_OUT = None
+
+
+def _claim_stdout() -> None:
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
@@ -197,7 +217,7 @@ def run_reference(args):
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -389,7 +409,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             b = cpu_baseline_sample()
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     sr.close()
     if world > 1:
         dist.barrier()
@@ -436,11 +456,11 @@ def run_julia(args):
     if args.impl == "reference":
         if rank == 0:
             b = julia_cpu_baseline(steps=args.steps)
-            print(json.dumps({"impl": "reference", "metric": "julia_8k_samples_per_s", "value": b["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            emit({"impl": "reference", "metric": "julia_8k_samples_per_s", "value": b["value"], "unit": "samples/s", "n_gpus": args.gpus,
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": b["seconds_per_step"] * 1e3, "higher_is_better": True,
                               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": J_WORKLOAD},
                               "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                              "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+                              "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         return 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — librmdf_b200 has no CPU fallback")
@@ -524,12 +544,12 @@ def run_julia(args):
                         "d2h_bytes_per_step": J_OUT_W * J_OUT_H * 4},
                 "gpu_launches": args.steps, "iterations_per_frame": int(its.item()),
                 "roofline": {"bound": "fp32_fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                             "kernel_ms": float(kt.item()), "note": "13 flop per z <- z^2 + c iteration; ncu: ALU pipe (compares, counters) is the busiest, see profiles/r1_julia_v2.md"},
+                             "kernel_ms": float(kt.item()), "note": "13 flop per z <- z^2 + c iteration; 3.8 iterations per sample on this frame, so per-sample bookkeeping weighs as much as the orbit (ncu: profiles/r1_julia_v3_packed.md)"},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             b = julia_cpu_baseline()
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     if shared is not None:
         torch.cuda.synchronize(); dist.barrier(); shared.close()
     sr.close()
@@ -551,6 +571,7 @@ def main():
     ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
                     help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "julia8k" and (args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus == 1):
         return run_julia(args)
@@ -561,7 +582,7 @@ def main():
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
-        return subprocess.call(cmd)
+        return subprocess.call(cmd, stdout=_RESULT_OUT)
     return run_julia(args) if args.workload == "julia8k" else run_ours(args)
 
 

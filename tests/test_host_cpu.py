@@ -147,12 +147,15 @@ def test_tile_dealing_and_assembly(R):
             tiles = frame.reshape(gy, h // gy, gx, w // gx).transpose(0, 2, 1, 3).reshape(gx * gy, h // gy, w // gx)
             packed = [tiles[o].reshape(-1) for o in owned]
             assert np.array_equal(par.assemble_tiles_numpy(packed, w, h, g, grid, skew), frame)
-    assert par.julia_band_height(34560, 3, 8) == 480 and par.julia_band_height(34560, 3, 1) % 32 == 0
+    assert par.julia_band_height(34560, 3, 8) == 96 and par.julia_band_height(34560, 3, 1) % 32 == 0      # 45 bands per rank
     bands = [np.full((2, 4, 6), r) for r in range(3)]          # 3 ranks × 2 bands × 4 rows × 6 px
     fr = par.assemble_bands_numpy([b.reshape(-1) for b in bands], 6, 24, 3, 4)
     assert fr[:, 0].tolist() == [0] * 4 + [1] * 4 + [2] * 4 + [0] * 4 + [1] * 4 + [2] * 4
-    assert par.balanced_grid(15360, 8640, 2, 8) == ((32, 16), 2)
-    assert par.balanced_grid(15360, 8640, 2, 2) == ((32, 16), 1)
+    # finest grid of >= 64-sample tiles on even pixel boundaries, gx a multiple of the world size, skew G/2
+    assert par.balanced_grid(15360, 8640, 2, 8) == ((240, 135), 4)
+    assert par.balanced_grid(15360, 8640, 2, 2) == ((240, 135), 1)
+    (gx, gy), skew = par.balanced_grid(1024, 512, 2, 4)
+    assert gx % 4 == 0 and 1024 % (2 * gx) == 0 and 512 % (2 * gy) == 0 and (1024 // gx) % 4 == 0 and (512 // gy) % 4 == 0
 
 
 _GLOO_WORKER = r'''
