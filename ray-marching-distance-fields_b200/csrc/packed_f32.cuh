@@ -24,4 +24,15 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 fma2(float a, f2 b, f2 c) { return __ffma2_rn(F2(a), b, c); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, float c) { return __ffma2_rn(a, b, F2(c)); }
 
+// ---- IEEE-exact use (the -fmad=false units) -----------------------------------------------------------
+// HAZARD: ptxas 12.9 contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even under --fmad=false (the scalar
+// .rn forms are never contracted) when the product has a single use and feeds the add directly; that changes
+// roundings.  julia.cu is safe by construction — every product there has two uses or feeds another product —
+// and tests/test_host_cpu.py disassembles the built -fmad=false objects and fails if any FFMA2 appears in
+// them.  Where a single-use product must feed a sum, write a + b as fma(−a, −1, b): (−a)·(−1) is exact, the
+// result is RN(a + b) bit for bit, and the product sits in the ADDEND, where there is nothing to contract
+// (with an immediate addend ptxas folds the −1 away again: use two scalar __fadd_rn there).  This was used
+// for a paired evaluation of the literal power-8 estimator in the parity build (bit-identical, but no faster:
+// profiles/r1_packed_fp32.md).
+
 }  // namespace rmdf

@@ -41,6 +41,30 @@ def test_library_exports_every_declared_symbol(R):
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure path")
+def test_ieee_units_have_no_packed_contraction(R):
+    """The bit-exact units are compiled -fmad=false, but ptxas contracts the PACKED forms mul.rn.f32x2 +
+    add.rn.f32x2 into FFMA2 regardless (csrc/packed_f32.cuh).  Disassemble the built objects: the Julia and
+    parity-march units must hold no packed FMA, while the fast unit must hold them (its iteration is built on
+    FFMA2/FMUL2) — a check that the disassembly itself works."""
+    import shutil
+    R._capi.load(build_if_missing=True)
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    objdir = ROOT / "ray-marching-distance-fields_b200" / "build"
+
+    def ops(name):
+        sass = subprocess.run([cuobjdump, "-sass", str(objdir / name)], capture_output=True, text=True, check=True).stdout
+        return re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", sass, flags=re.M)
+
+    for unit in ("julia.cu.o", "march_parity.cu.o"):
+        o = ops(unit)
+        assert len(o) > 1000 and "FFMA2" not in o, "%s: ptxas contracted a packed multiply-add" % unit
+    assert "FMUL2" in ops("julia.cu.o") and "FADD2" in ops("julia.cu.o")
+    fast = ops("march_fast.cu.o")
+    assert "FFMA2" in fast and "FMUL2" in fast
+
+
 def test_no_cpu_fallback(R):
     with pytest.raises(R.RmdfError) as e:
         R.ShaderRenderer(0)
