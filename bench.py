@@ -502,6 +502,11 @@ def run_julia(args):
         return par.gather_bands(out_dev, J_OUT_W, J_OUT_H, world, rank, band_h >> J_SPP_LOG2, gather_list)
 
     def step_e2e():
+        if world == 1:                                                  # the reference-facing call: host buffer in, frame out
+            import ctypes as C
+            R._capi.check(sr._lib.rmdf_julia(sr.handle, J_FB_W, J_FB_H, 0, C.c_double(J_TICK), 0, J_FB_H, J_SPP_LOG2,
+                                             C.c_void_p(frame_host.data_ptr())))
+            return
         frame = step_resident()
         if rank == 0:
             frame_host.copy_(frame.reshape(-1), non_blocking=True)

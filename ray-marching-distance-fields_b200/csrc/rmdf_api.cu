@@ -636,6 +636,18 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     return RMDF_OK;
 }
 
+// A host buffer the device can write directly: page-locked memory (cudaHostAlloc / cudaHostRegister — e.g. a
+// pinned Storable vector or torch pin_memory) is mapped into the device's address space under UVA.  The kernels then
+// store resolved pixels straight into it over PCIe while they run, and the separate device→host copy of the frame
+// (33 MB for BASELINE config 4: 18.2 → 17.7 ms end to end) disappears.  Pageable memory → NULL.
+static void *device_view_of_host(const void *host)
+{
+    if (getenv("RMDF_NO_ZERO_COPY")) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+}
+
 extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
 {
     int rc = use(ctx); if (rc) return rc;
@@ -645,6 +657,11 @@ extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const size_t px_bytes = (p->out_format == RMDF_OUT_RGBA32F) ? 16 : 4;
     const size_t bytes = (size_t)wl.out_pixels * px_bytes;
+    if (void *direct = device_view_of_host(fb_host)) {     // page-locked frame buffer: the kernel's stores are the copy
+        if ((rc = rmdf_render_device(ctx, p, direct))) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        return RMDF_OK;
+    }
     if ((rc = ensure_staging(ctx, bytes))) return rc;
     const bool partial = wl.rect_mode != 0 && p->layout == RMDF_LAYOUT_FRAME;
     if (partial)   // drawShaderTile leaves the rest of the FBO untouched: start from the caller's pixels
@@ -747,6 +764,8 @@ extern "C" int rmdf_julia(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
     if (resolve_log2 < 0 || resolve_log2 > 3 || y1 <= y0 || w < 1) return fail(RMDF_ERR_ARG, "rmdf_julia: bad arguments");
     const size_t bytes = sizeof(uint32_t) * (size_t)(w >> resolve_log2) * (size_t)((y1 - y0) >> resolve_log2);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    // (no direct stores into page-locked memory here, unlike rmdf_render: the Julia kernel emits 25 GB/s of 16-byte
+    //  row fragments — measured on config 5: 10.4 ms direct against 7.7 ms through the staging buffer + one copy)
     if ((rc = ensure_staging(ctx, bytes))) return rc;
     if ((rc = rmdf_julia_device(ctx, w, h, smooth, tick, y0, y1, resolve_log2, ctx->d_out))) return rc;
     CU(cudaMemcpyAsync(fb_host, ctx->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -87,3 +87,32 @@ def test_counters_accumulate_and_reset(sr, R):
     assert sr.counters()["samples"] == 0
     pk = sr.measureFp32Peak()
     assert 30.0 < pk["tflops"] < 90.0                              # 148 SM × 128 lanes × 2 × ~1.9 GHz ≈ 72
+
+
+def test_page_locked_host_buffers_are_written_in_place(sr, O, R, oracle_envs):
+    """rmdf_render with a page-locked host buffer: the kernel stores straight into it (no staging copy); the
+    pixels are the same as through pageable memory and a tile leaves the rest of the buffer alone.  rmdf_julia
+    accepts page-locked memory too (through its staging buffer)."""
+    import torch
+    for s in range(5):
+        sr.bindCubeMap(s, oracle_envs[s])
+    w, h, k = 512, 256, 1
+    want = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)      # pageable numpy buffer
+    pinned = torch.full(((h >> k) * (w >> k),), 0x55, dtype=torch.int32).pin_memory()
+    p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+    sr.renderHost(p, pinned.data_ptr())
+    assert np.array_equal(pinned.numpy().view(np.uint32).reshape(h >> k, w >> k), want)
+    # one tile of the reference's 8×8 grid into a pre-filled pinned frame: everything else keeps the caller's value
+    pinned.fill_(0x55)
+    pt = sr.makeParams(R.FragmentShader.FSMBPower8Shader, 27, w, h, 0.0, resolve_log2=k)
+    sr.renderHost(pt, pinned.data_ptr())
+    got = pinned.numpy().view(np.uint32).reshape(h >> k, w >> k)
+    tw, th = (w >> k) // 8, (h >> k) // 8
+    tx, ty = 27 % 8, 27 // 8
+    mask = np.zeros_like(got, bool); mask[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw] = True
+    assert np.array_equal(got[mask], want[mask]) and (got[~mask] == 0x55).all()
+    # Julia
+    jw, jh = 256, 144
+    jp = torch.zeros(jw * jh, dtype=torch.int32).pin_memory()
+    R._capi.check(sr._lib.rmdf_julia(sr.handle, jw, jh, 0, C.c_double(7.0), 0, jh, 0, C.c_void_p(jp.data_ptr())))
+    assert np.array_equal(jp.numpy().view(np.uint32).reshape(jh, jw), O.julia(jw, jh, False, 7.0))
