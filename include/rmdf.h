@@ -159,7 +159,9 @@ typedef struct {
  * number of tiles it renders; for sizing the caller's buffer. */
 int64_t rmdf_render_output_pixels(const rmdf_params *p, int32_t *n_tiles);
 /* Render into host memory (the MVector Word32 of fillFrameBuffer, FrameBuffer.hs:117-
- * 135).  Includes the device→host copy; returns when `fb` is complete. */
+ * 135); returns when `fb` is complete.  Pageable memory goes through a device staging
+ * buffer and one device→host copy; page-locked memory (cudaHostAlloc / cudaHostRegister,
+ * like the mapped PBO the reference hands out) is written directly by the kernel. */
 int  rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host);
 /* Render into device memory on ctx's device; asynchronous on the context's stream. */
 int  rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_dev);
