@@ -281,6 +281,18 @@ def run_ours(args):
         if shared is None:
             p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
                               shard_rank=rank, shard_count=world, layout=R.LAYOUT_PACKED_TILES, shard_grid=grid, shard_skew=skew)
+    # end to end at N > 1: the shared frame in page-locked HOST memory, written by every rank's kernel directly
+    host_shared = None
+    if shared is not None:
+        try:
+            host_shared = par.SharedHostFrame(sr, OUT_W * OUT_H, world, rank)
+        except (R.RmdfError, OSError) as e:
+            if rank == 0:
+                print("bench.py: shared host frame unavailable (%s); end to end = peer frame + D2H copy" % e, file=sys.stderr)
+        okh = torch.tensor([1 if host_shared is not None else 0], device=dev)
+        dist.all_reduce(okh, op=dist.ReduceOp.MIN)
+        if int(okh.item()) == 0 and host_shared is not None:
+            host_shared.close(); host_shared = None
     n_out, n_tiles = sr.outputPixels(p)
     out_dev = torch.empty(n_out if shared is None else 1, dtype=torch.int32, device=dev)
     shared_frame = shared.as_tensor() if (shared is not None and rank == 0) else None
@@ -310,6 +322,9 @@ def run_ours(args):
             R._capi.check(sr._lib.rmdf_envmap_bind_cube(sr.handle, s, c.data_ptr(), c.shape[1]))
         if not sharded:
             sr.renderHost(p, frame_host.data_ptr())                     # kernel + D2H through the C ABI
+        elif host_shared is not None:
+            sr.renderDevice(p, host_shared.ptr)                         # every rank stores its tiles into the host frame
+            host_shared.complete()                                      # sync + one barrier: the frame is in host memory
         else:
             frame = step_resident()
             if rank == 0:
@@ -342,6 +357,11 @@ def run_ours(args):
     launches = (c["launches"] - l0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    e2e_same = None
+    if host_shared is not None:                       # the host frame the e2e path produced == the device-resident frame
+        step_resident(); step_e2e(); barrier()
+        if rank == 0:
+            e2e_same = bool(np.array_equal(host_shared.as_numpy().view(np.int32), shared_frame.cpu().numpy()))
 
     # per-launch kernel time and counters for the roofline (rank-local kernel, all ranks reduced)
     per = args.steps + args.warmup
@@ -390,7 +410,10 @@ def run_ours(args):
                        "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": ("tiles %dx%d, rank = (tx + %d*ty) mod %d, %s" % (grid[0], grid[1], skew, world, "tile stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if sharded else "single GPU",
                        "l2": "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4},
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4,
+                    "path": ("rmdf_render with a page-locked host frame buffer: the kernel's stores are the D2H" if not sharded else
+                             ("every rank's kernel stores its tiles into one page-locked host frame (POSIX shm) over its own PCIe link + barrier; frame equals the device-resident one: %s" % e2e_same) if host_shared is not None
+                             else "device-resident gather + D2H copy on rank 0")},
             "gpu_launches": int(launches),
             "sdf_steps_per_s": (frame_cnt["march_de"] + frame_cnt["shade_de"]) / (ms_res * 1e-3),
             "frame_counters": {k: int(v) for k, v in frame_cnt.items()},
@@ -410,6 +433,10 @@ def run_ours(args):
             b = cpu_baseline_sample()
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
+    if host_shared is not None:
+        host_shared.close()
+    if shared is not None:
+        torch.cuda.synchronize(); dist.barrier(); shared.close()
     sr.close()
     if world > 1:
         dist.barrier()

@@ -202,6 +202,12 @@ int  rmdf_shared_free(rmdf_ctx *ctx, void *dev_ptr);
 int  rmdf_shared_open(rmdf_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
 int  rmdf_shared_close(rmdf_ctx *ctx, void *dev_ptr);
 int  rmdf_enable_peer(rmdf_ctx *ctx, int peer_device);
+/* A frame buffer in HOST memory that several processes' kernels write into: page-lock `bytes` at `host_ptr`
+ * (e.g. a POSIX shared-memory mapping that every rank has opened) for ctx's device and return the address the
+ * device uses for it; pass that as `fb_dev` with RMDF_LAYOUT_FRAME + shard_*.  Each GPU then stores its tiles
+ * over its own PCIe link straight into the final host frame: no gather and no device→host copy on rank 0. */
+int  rmdf_host_register(rmdf_ctx *ctx, void *host_ptr, int64_t bytes, void **dev_ptr);
+int  rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr);
 
 /* ---- counters (new; the reference only prints FPS, App.hs:221-238) ------------- */
 typedef struct {

@@ -26,6 +26,7 @@ EXPORTS = [
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
     "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak",
     "rmdf_shared_alloc", "rmdf_shared_free", "rmdf_shared_open", "rmdf_shared_close", "rmdf_enable_peer",
+    "rmdf_host_register", "rmdf_host_unregister",
 ]
 
 
@@ -104,6 +105,8 @@ def load(build_if_missing: bool = True):
     L.rmdf_shared_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.rmdf_shared_close.argtypes = [vp, vp]
     L.rmdf_enable_peer.argtypes = [vp, C.c_int]
+    L.rmdf_host_register.argtypes = [vp, vp, C.c_int64, C.POINTER(vp)]
+    L.rmdf_host_unregister.argtypes = [vp, vp]
     for name in EXPORTS:
         f = getattr(L, name)
         if name not in ("rmdf_destroy", "rmdf_last_error", "rmdf_render_output_pixels"):

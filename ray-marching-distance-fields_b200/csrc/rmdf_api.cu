@@ -836,6 +836,25 @@ extern "C" int rmdf_enable_peer(rmdf_ctx *ctx, int peer_device)
     return RMDF_OK;
 }
 
+extern "C" int rmdf_host_register(rmdf_ctx *ctx, void *host_ptr, int64_t bytes, void **dev_ptr)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!host_ptr || !dev_ptr || bytes <= 0) return fail(RMDF_ERR_ARG, "rmdf_host_register: bad arguments");
+    cudaError_t e = cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RMDF_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    e = cudaHostGetDevicePointer(dev_ptr, host_ptr, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(host_ptr); cudaGetLastError(); return fail(RMDF_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); }
+    return RMDF_OK;
+}
+extern "C" int rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr)
+{
+    int rc = use(ctx); if (rc) return rc;
+    if (!host_ptr) return fail(RMDF_ERR_ARG, "rmdf_host_unregister: NULL");
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaHostUnregister(host_ptr));
+    return RMDF_OK;
+}
+
 // ---- measurement ----------------------------------------------------------------------------
 extern "C" int rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz)
 {

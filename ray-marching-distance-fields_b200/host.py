@@ -395,6 +395,15 @@ class ShaderRenderer:
     def enablePeer(self, peer_device: int) -> None:
         check(self._lib.rmdf_enable_peer(self._h, peer_device))
 
+    def hostRegister(self, host_ptr: int, nbytes: int) -> int:
+        """Page-lock host memory for this context's device; returns the device-side address of it."""
+        ptr = C.c_void_p()
+        check(self._lib.rmdf_host_register(self._h, C.c_void_p(host_ptr), nbytes, C.byref(ptr)))
+        return int(ptr.value)
+
+    def hostUnregister(self, host_ptr: int) -> None:
+        check(self._lib.rmdf_host_unregister(self._h, C.c_void_p(host_ptr)))
+
     # -- counters ------------------------------------------------------------------------
     def counters(self) -> dict:
         c = Counters()

@@ -170,3 +170,57 @@ class SharedFrame:
             self.sr.sharedFree(self.ptr)
         elif self.world > 1:
             self.sr.sharedClose(self.ptr)
+
+
+class SharedHostFrame:
+    """The end-to-end variant of SharedFrame: the resolved frame lives in HOST memory (one POSIX shared-memory
+    segment that every rank maps and page-locks for its own GPU, `rmdf_host_register`).  Every rank's kernel
+    stores its tiles over its own PCIe link straight into the final host frame, so after the launch there is
+    one barrier and nothing else — no gather, and no device→host copy on rank 0 (33 MB per config-4 frame)."""
+
+    def __init__(self, sr, n_words: int, world: int, rank: int):
+        import ctypes as C
+        from multiprocessing import shared_memory
+        import torch.distributed as dist
+        self.sr, self.world, self.rank, self.n_words = sr, world, rank, n_words
+        box = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=n_words * 4)
+            box[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                self.shm = shared_memory.SharedMemory(name=box[0])
+                try:                 # only the creator unlinks: keep Python's resource tracker from trying again at exit
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
+        self.host_ptr = C.addressof(C.c_char.from_buffer(self.shm.buf))
+        self.ptr = sr.hostRegister(self.host_ptr, n_words * 4)
+
+    def complete(self):
+        """Every rank: its kernel has finished (stream synchronised) and so have all the others'."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def as_numpy(self):
+        """Rank 0: the frame as a uint32 array over the shared segment (no copy)."""
+        return np.frombuffer(self.shm.buf, dtype=np.uint32, count=self.n_words)
+
+    def close(self):
+        import torch.distributed as dist
+        self.sr.hostUnregister(self.host_ptr)
+        if self.world > 1:
+            dist.barrier()
+        self.host_ptr = None
+        try:
+            self.shm.close()
+        except BufferError:          # a numpy view is still alive; the mapping goes with the process
+            pass
+        if self.rank == 0:
+            self.shm.unlink()

@@ -116,3 +116,24 @@ def test_page_locked_host_buffers_are_written_in_place(sr, O, R, oracle_envs):
     jp = torch.zeros(jw * jh, dtype=torch.int32).pin_memory()
     R._capi.check(sr._lib.rmdf_julia(sr.handle, jw, jh, 0, C.c_double(7.0), 0, jh, 0, C.c_void_p(jp.data_ptr())))
     assert np.array_equal(jp.numpy().view(np.uint32).reshape(jh, jw), O.julia(jw, jh, False, 7.0))
+
+
+def test_host_registered_frame_buffer(sr, R, oracle_envs):
+    """rmdf_host_register: ordinary host memory (here a numpy array; in the multi-rank bench a POSIX shared-memory
+    segment) page-locked for the device and used as the render target of rmdf_render_device — what every rank
+    does with the shared host frame (parallel.SharedHostFrame)."""
+    for s in range(5):
+        sr.bindCubeMap(s, oracle_envs[s])
+    w, h, k = 512, 256, 1
+    want = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+    buf = np.zeros((h >> k, w >> k), np.uint32)
+    dev_ptr = sr.hostRegister(buf.ctypes.data, buf.nbytes)
+    try:
+        for rank in range(2):                                   # two "ranks" fill their tiles of the same host frame
+            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k, shard_rank=rank, shard_count=2,
+                              shard_grid=(16, 8), shard_skew=1)
+            sr.renderDevice(p, dev_ptr)
+        sr.sync()
+    finally:
+        sr.hostUnregister(buf.ctypes.data)
+    assert np.array_equal(buf, want)
