@@ -203,10 +203,13 @@ class SharedHostFrame:
         """Every rank: its kernel has finished (stream synchronised) and so have all the others'."""
         import torch
         import torch.distributed as dist
-        torch.cuda.synchronize()
+        cuda = torch.cuda.is_available()             # (the CPU test drives this class with gloo and no device)
+        if cuda:
+            torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+            if cuda:
+                torch.cuda.synchronize()
 
     def as_numpy(self):
         """Rank 0: the frame as a uint32 array over the shared segment (no copy)."""

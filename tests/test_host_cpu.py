@@ -198,9 +198,24 @@ mine = torch.from_numpy(np.ascontiguousarray(tiles[par.tiles_of_rank(rank, world
 out = par.gather_frame(mine, w, h, world, rank, grid=grid, skew=skew)
 if rank == 0:
     assert out is not None and np.array_equal(out.numpy(), frame), "assembled frame differs"
-    print("GLOO_OK")
 else:
     assert out is None
+# the shared HOST frame of the end-to-end path: one POSIX shm segment, every rank writes its tiles in place
+class FakeRenderer:                       # stands in for the CUDA context: "registering" returns the host address
+    def hostRegister(self, ptr, nbytes): return ptr
+    def hostUnregister(self, ptr): pass
+sh = par.SharedHostFrame(FakeRenderer(), w * h, world, rank)
+view = np.frombuffer(sh.shm.buf, dtype=np.int32, count=w * h).reshape(h, w)
+tw, th = w // grid[0], h // grid[1]
+for t in par.tiles_of_rank(rank, world, grid, skew):
+    ty, tx = divmod(t, grid[0])
+    view[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw] = frame[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+sh.complete()
+if rank == 0:
+    assert np.array_equal(sh.as_numpy().view(np.int32).reshape(h, w), frame), "shared host frame differs"
+    print("GLOO_OK")
+del view
+sh.close()
 dist.barrier(); dist.destroy_process_group()
 '''
 
