@@ -438,6 +438,16 @@ extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
         const rg_vec3 c = rg_v3((v0.x + v1.x + v2.x) / 3.0f, (v0.y + v1.y + v2.y) / 3.0f, (v0.z + v1.z + v2.z) / 3.0f);
         const float rad = fmaxf(rg_length(rg_sub(v0, c)), fmaxf(rg_length(rg_sub(v1, c)), rg_length(rg_sub(v2, c))));
         r[6] = make_float4(c.x, c.y, c.z, rad * 1.0001f + 1.0e-5f);
+        // supporting plane (unit normal n, offset −n·v0) in double precision: |n·p + w| is a lower bound of the
+        // distance to the triangle — the second exact culling test (a wall far away has a huge sphere but a far plane)
+        {
+            const double ax = (double)v1.x - v0.x, ay = (double)v1.y - v0.y, az = (double)v1.z - v0.z;
+            const double bx = (double)v2.x - v0.x, by = (double)v2.y - v0.y, bz = (double)v2.z - v0.z;
+            double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+            const double l = sqrt(nx * nx + ny * ny + nz * nz);
+            if (l > 0.0) { nx /= l; ny /= l; nz /= l; } else { nx = ny = nz = 0.0; }      // degenerate: plane test never culls
+            r[7] = make_float4((float)nx, (float)ny, (float)nz, (float)-(nx * v0.x + ny * v0.y + nz * v0.z));
+        }
     }
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));

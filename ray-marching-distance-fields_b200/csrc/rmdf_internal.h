@@ -12,7 +12,7 @@ constexpr int kBlockDim     = 32;    // a work item is a 32×32 block of frame-b
 #endif
 constexpr int kWarpsPerCta  = RMDF_WARPS_PER_CTA;
 constexpr int kCtaThreads   = kWarpsPerCta * 32;
-constexpr int kCornellStride = 7;     // float4 per triangle: 6 of precomputed terms + bounding sphere
+constexpr int kCornellStride = 8;     // float4 per triangle: 6 of precomputed terms + bounding sphere + plane
 constexpr int kCornellF4    = 32 * kCornellStride;
 
 enum CounterSlot { C_SAMPLES = 0, C_IN_SPHERE, C_HITS, C_MARCH_DE, C_SHADE_DE, C_ITERS, C_NSLOTS = 8 };
