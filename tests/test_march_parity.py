@@ -236,6 +236,31 @@ def test_shader_options_bit_exact(sr, O, R, oracle_envs, scene, flags):
     assert np.mean((fast[..., 3] > 0.5) == ref["hit"].astype(bool)) > 0.995
 
 
+@pytest.mark.parametrize("time", [0.0, 3.3, 11.7])
+@pytest.mark.parametrize("flags", [0, 1, 2])
+def test_cornell_exact_culling(sr, O, R, oracle_envs, time, flags):
+    """de_cornell_box skips triangles by three exact tests (supporting plane, bounding sphere, an upper bound
+    that starts from the caller's Lipschitz hint and tightens with every evaluated distance): the result must be
+    the minimum over all 32 triangles bit for bit — colour, hit mask and work counters equal the oracle's, which
+    evaluates every triangle — for several cameras, with central-difference normals (no hint on those calls) and
+    with the orthographic camera (parallel rays)."""
+    _bind(sr, oracle_envs)
+    w, h = 320, 180
+    ref = O.render(0, w, h, time, envs=oracle_envs, flags=flags)
+    sr.resetCounters()
+    got = sr.drawShaderTile(R.FragmentShader.FSDECornellBoxShader, None, w, h, time, flags=flags, out_format=R.OUT_RGBA32F)
+    assert np.array_equal(got[..., 3] > 0.5, ref["hit"].astype(bool))
+    assert np.array_equal(got[..., :3].view(np.uint32), ref["linear"].view(np.uint32))
+    c, rc = sr.counters(), ref["counters"]
+    assert (c["samples"], c["in_sphere"], c["hits"], c["march_de"], c["shade_de"]) == \
+           (rc["samples"], rc["in_sphere"], rc["hits"], rc["march_de"], rc["shade_de"])
+    fast = sr.drawShaderTile(R.FragmentShader.FSDECornellBoxShader, None, w, h, time, flags=flags, out_format=R.OUT_RGBA32F, mode=R.MODE_FAST)
+    agree = np.mean((fast[..., 3] > 0.5) == ref["hit"].astype(bool))
+    p = psnr(np.clip(np.nan_to_num(fast[..., :3]), 0, 1), np.clip(np.nan_to_num(ref["linear"]), 0, 1))
+    print("cornell fast t=%g flags=%d: hit agreement %.5f%%, linear PSNR %.2f dB" % (time, flags, agree * 100, p))
+    assert agree >= 0.999 and p >= 35.0
+
+
 def test_error_behaviour(sr, R):
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(5, None, 64, 64, 0.0)
