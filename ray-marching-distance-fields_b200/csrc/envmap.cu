@@ -24,6 +24,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
 #include "rmdf_internal.h"
 
 namespace rmdf {
@@ -144,7 +147,18 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
     const size_t ntab = (size_t)w * w;
     float *host = (float *)malloc(sizeof(float) * (ntab + 2 * (size_t)h));
     if (!host) return cudaErrorMemoryAllocation;
-    convolve_tables(w, h, host, host + ntab, host + ntab + h);
+    {   // the tables depend on (w, h) only: w² + 2h libm calls, kept for the next sweep of the same size
+        static std::mutex mu;
+        static std::vector<float> cached;
+        static int cached_w = 0, cached_h = 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (cached_w != w || cached_h != h) {
+            cached.resize(ntab + 2 * (size_t)h);
+            convolve_tables(w, h, cached.data(), cached.data() + ntab, cached.data() + ntab + h);
+            cached_w = w; cached_h = h;
+        }
+        memcpy(host, cached.data(), sizeof(float) * (ntab + 2 * (size_t)h));
+    }
     float *d_tab = nullptr, *d_partial = nullptr;
     const int splits = 4, rows_per_split = (h + splits - 1) / splits;
     const size_t npix = (size_t)w * h;
