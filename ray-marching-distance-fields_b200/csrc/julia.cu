@@ -64,14 +64,24 @@ __device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2
     }
 // The reference's 1-cycle test (newZ == z ⇒ maxIter) is only a shortcut: a repeating orbit never escapes, so it
 // ends at maxIter with the same z either way.  Testing once per block of eight iterations for
-// z == z(block start) catches every cycle whose period divides 8 — same result (maxIter), one compare pair per
-// eight iterations instead of per iteration.
+// z == z(block start) catches every cycle whose period divides the block length — same result (maxIter), one
+// compare pair per block instead of per iteration.
 #define RMDF_JULIA_PERIODIC(sr, si)                                                               \
     {                                                                                             \
         if (zr.x == (sr).x && zi.x == (si).x) { done |= 1u; jr.x = kNaN; }                        \
         if (zr.y == (sr).y && zi.y == (si).y) { done |= 2u; jr.y = kNaN; }                        \
         if (done == 3u) goto finished;                                                            \
     }
+
+#ifndef RMDF_JULIA_BLOCK_LEN
+#define RMDF_JULIA_BLOCK_LEN 8     // iterations between periodicity tests (a divisor of 40): 4 or 8
+#endif
+#if RMDF_JULIA_BLOCK_LEN == 8
+#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_STEP(b) RMDF_JULIA_STEP((b) + 1) RMDF_JULIA_STEP((b) + 2) RMDF_JULIA_STEP((b) + 3) \
+                            RMDF_JULIA_STEP((b) + 4) RMDF_JULIA_STEP((b) + 5) RMDF_JULIA_STEP((b) + 6) RMDF_JULIA_STEP((b) + 7)
+#else
+#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_STEP(b) RMDF_JULIA_STEP((b) + 1) RMDF_JULIA_STEP((b) + 2) RMDF_JULIA_STEP((b) + 3)
+#endif
 
 template <bool SMOOTH>
 __global__ void __launch_bounds__(kCtaThreads, 8)
@@ -135,17 +145,15 @@ julia_kernel(const JuliaParams P)
                     int it0 = 40, it1 = 40;
                     float m0 = 0.0f, m1 = 0.0f;                                      // |z|² at the escape
                     unsigned done = live ^ 3u;
-                    // iterations 0..7: the block's start value is (xs, ys) itself
-                    RMDF_JULIA_STEP(0) RMDF_JULIA_STEP(1) RMDF_JULIA_STEP(2) RMDF_JULIA_STEP(3)
-                    RMDF_JULIA_STEP(4) RMDF_JULIA_STEP(5) RMDF_JULIA_STEP(6) RMDF_JULIA_STEP(7)
+                    // first block: its start value is (xs, ys) itself
+                    RMDF_JULIA_BLOCK(0)
                     RMDF_JULIA_PERIODIC(xs[c], ys)
                     {
-                        int base = 8;
+                        int base = RMDF_JULIA_BLOCK_LEN;
 #pragma unroll 1
-                        for (; base < 40; base += 8) {
+                        for (; base < 40; base += RMDF_JULIA_BLOCK_LEN) {
                             const f2 sr0 = zr, si0 = zi;
-                            RMDF_JULIA_STEP(base)     RMDF_JULIA_STEP(base + 1) RMDF_JULIA_STEP(base + 2) RMDF_JULIA_STEP(base + 3)
-                            RMDF_JULIA_STEP(base + 4) RMDF_JULIA_STEP(base + 5) RMDF_JULIA_STEP(base + 6) RMDF_JULIA_STEP(base + 7)
+                            RMDF_JULIA_BLOCK(base)
                             RMDF_JULIA_PERIODIC(sr0, si0)
                         }
                     }
@@ -203,6 +211,7 @@ julia_kernel(const JuliaParams P)
         atomicAdd(P.counters + C_ITERS, (unsigned long long)iters);
     }
 }
+#undef RMDF_JULIA_BLOCK
 #undef RMDF_JULIA_STEP
 #undef RMDF_JULIA_PERIODIC
 
