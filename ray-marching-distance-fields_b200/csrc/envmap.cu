@@ -145,28 +145,30 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
 {
     cudaError_t e;
     const size_t ntab = (size_t)w * w;
-    float *host = (float *)malloc(sizeof(float) * (ntab + 2 * (size_t)h));
-    if (!host) return cudaErrorMemoryAllocation;
-    {   // the tables depend on (w, h) only: w² + 2h libm calls, kept for the next sweep of the same size
+    const size_t nall = ntab + 2 * (size_t)h;
+    // The tables depend on (w, h) only — w² + 2h libm calls and a 260 KB upload — so the device copy is kept per
+    // (device, w, h) for the next sweep of the same size (a few sizes at most: never freed before exit).
+    float *d_tab = nullptr;
+    {
+        struct Entry { int dev, w, h; float *d; };
         static std::mutex mu;
-        static std::vector<float> cached;
-        static int cached_w = 0, cached_h = 0;
+        static std::vector<Entry> cache;
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         std::lock_guard<std::mutex> lk(mu);
-        if (cached_w != w || cached_h != h) {
-            cached.resize(ntab + 2 * (size_t)h);
-            convolve_tables(w, h, cached.data(), cached.data() + ntab, cached.data() + ntab + h);
-            cached_w = w; cached_h = h;
+        for (const Entry &c : cache) if (c.dev == dev && c.w == w && c.h == h) d_tab = c.d;
+        if (!d_tab) {
+            std::vector<float> host(nall);
+            convolve_tables(w, h, host.data(), host.data() + ntab, host.data() + ntab + h);
+            if ((e = cudaMalloc(&d_tab, sizeof(float) * nall)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(d_tab, host.data(), sizeof(float) * nall, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d_tab); return e; }
+            cache.push_back({ dev, w, h, d_tab });
         }
-        memcpy(host, cached.data(), sizeof(float) * (ntab + 2 * (size_t)h));
     }
-    float *d_tab = nullptr, *d_partial = nullptr;
+    float *d_partial = nullptr;
     const int splits = 4, rows_per_split = (h + splits - 1) / splits;
     const size_t npix = (size_t)w * h;
-    if ((e = cudaMallocAsync(&d_tab, sizeof(float) * (ntab + 2 * (size_t)h), s)) != cudaSuccess) { free(host); return e; }
-    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * splits * npix * 13, s)) != cudaSuccess) { cudaFreeAsync(d_tab, s); free(host); return e; }
-    e = cudaMemcpyAsync(d_tab, host, sizeof(float) * (ntab + 2 * (size_t)h), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // host table is freed below
-    free(host);
+    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * splits * npix * 13, s)) != cudaSuccess) return e;
     const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
     const dim3 grid((w + CV_DX - 1) / CV_DX, (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY, splits);
     for (int first = 0; first < np && e == cudaSuccess; first += 4) {
@@ -189,7 +191,6 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
         convolve_finish_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, s>>>(d_partial, (int)npix, splits, cnt, i0, i1, out_dev + (size_t)first * npix * 3);
         e = cudaGetLastError();
     }
-    cudaFreeAsync(d_tab, s);
     cudaFreeAsync(d_partial, s);
     return e;
 }
