@@ -33,13 +33,21 @@ __device__ __forceinline__ uint32_t j_box4_green(uint32_t a, uint32_t b, uint32_
 
 // pixel word of one sample: toGreen . truncate $ fromIntegral iCnt / 40 * 255 (Fractal2D.hs:93-97); the smooth
 // variant subtracts log(log |z|²)/log 2 at the escape (fractionalIterCnt, :24-25)
+// a / b for a divisor known in advance, correctly rounded (Markstein): with y = RN(1/b), q = RN(a·y) is within one ulp
+// of the quotient, r = a − b·q is exact in an FMA, and RN(q + r·y) is RN(a/b) for every b whose significand is not
+// all ones — three instructions instead of the ~12 of the general IEEE division sequence.
+__device__ __forceinline__ float div_known(float a, float b, float y)
+{
+    const float q = __fmul_rn(a, y);
+    return __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
+}
 template <bool SMOOTH>
-__device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2, const uint32_t *lut)
+__device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2, float rcp_log_2, const uint32_t *lut)
 {
     if (SMOOTH && iter != 40) {
-        const float v = (float)iter - rg_log(rg_log(mag2)) / log_2;
+        const float v = (float)iter - div_known(rg_log(rg_log(mag2)), log_2, rcp_log_2);
         const float ic = v > 0.0f ? v : 0.0f;
-        return ((uint32_t)(int)truncf(ic / 40.0f * 255.0f)) << 8;
+        return ((uint32_t)(int)truncf(div_known(ic, 40.0f, 0.025f) * 255.0f)) << 8;
     }
     return lut[iter];
 }
@@ -98,7 +106,7 @@ julia_kernel(const JuliaParams P)
     const int mx = lane & 7, my = lane >> 3;        // a warp covers 16×4 samples: lane = 2 adjacent columns of one row
     const float kNaN = __int_as_float(0x7fffffff);
     const int k = P.resolve_log2;
-    const float log_2 = rg_log(2.0f);
+    const float log_2 = rg_log(2.0f), rcp_log_2 = 1.0f / log_2;
     const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
@@ -158,9 +166,9 @@ julia_kernel(const JuliaParams P)
                         }
                     }
                 finished:
-                    w0 = julia_word<SMOOTH>(it0, m0, log_2, s_lut);
+                    w0 = julia_word<SMOOTH>(it0, m0, log_2, rcp_log_2, s_lut);
                     iters += (unsigned)it0; samples++;
-                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, s_lut); iters += (unsigned)it1; samples++; }
+                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, rcp_log_2, s_lut); iters += (unsigned)it1; samples++; }
                 }
                 if (live == 3u) *reinterpret_cast<uint2 *>(stage + ly * kBlockDim + lx) = make_uint2(w0, w1);
                 else if (live)  stage[ly * kBlockDim + lx] = w0;
