@@ -622,9 +622,20 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
 
     const int ctas_per_sm = (p->mode == RMDF_MODE_FAST) ? march_fast_ctas_per_sm(p->scene, p->flags) : march_parity_ctas_per_sm(p->scene, p->flags);
     const int resident_warps = ctas_per_sm * ctx->sm_count * kWarpsPerCta;
-    const int bx = (wl.tile_w + kBlockDim - 1) / kBlockDim;
+    int bx = (wl.tile_w + kBlockDim - 1) / kBlockDim;
     const int64_t blocks32 = (int64_t)bx * ((wl.tile_h + 31) / 32) * wl.n_tiles;
     mp.item_h = pick_item_h(blocks32, resident_warps, p->resolve_log2);
+    // A frame too small to give every resident warp a few items even at the smallest item height (BASELINE config 1:
+    // 512×512 = 2048 items of 32×4 samples for 4736 warps) gets narrower items too: 16 or 8 columns (one 8×4 tile row).
+    mp.item_w = kBlockDim;
+    {
+        const int min_h = (1 << p->resolve_log2) > 4 ? (1 << p->resolve_log2) : 4;
+        const int min_w = (1 << p->resolve_log2) > 8 ? (1 << p->resolve_log2) : 8;
+        while (mp.item_h == min_h && mp.item_w > min_w &&
+               (int64_t)((wl.tile_w + mp.item_w - 1) / mp.item_w) * ((wl.tile_h + mp.item_h - 1) / mp.item_h) * wl.n_tiles < (int64_t)resident_warps * 4)
+            mp.item_w >>= 1;
+        bx = (wl.tile_w + mp.item_w - 1) / mp.item_w;
+    }
     mp.blocks_x = bx;
     mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
     const int64_t n_items = (int64_t)mp.blocks_x * mp.blocks_y * wl.n_tiles;

@@ -33,6 +33,7 @@ struct MarchParams {
     int   shard_gx, shard_count, shard_rank, shard_skew, shard_ty0;   // shard_ty0: first tile row of a stripe
     int   tile_w, tile_h;             // level-0 size of one tile
     int   item_h;                     // rows per work item: 4, 8, 16 or 32
+    int   item_w;                     // columns per work item: 32, or 16 / 8 on frames too small to fill the machine
     int   blocks_x, blocks_y;         // 32×item_h blocks per rect
     int   n_items;
     int   out_stride;                 // output row stride in pixels (already >> resolve_log2)
