@@ -43,6 +43,21 @@ float oracle_mb_power(float in_time);
 float oracle_distance(int scene, float in_time, const float *cornell, float x, float y, float z);
 void  oracle_glsl_eval(int fn, const float *x, const float *y, float *out, int64_t n);
 
+/* single functions of fragment.shd over n inputs (lattice tests against oracle/_ref) */
+void oracle_distance_n(int scene, float in_time, const float *cornell, const float *pts, float *out, int64_t n);
+void oracle_ray_march_n(int scene, float in_time, const float *cornell, const float *origins, const float *dirs, float *out /*n·(hit,t)*/, int64_t n);
+void oracle_normal_n(int scene, float in_time, const float *cornell, int central, const float *pts, float *out, int64_t n);
+void oracle_distance_ao_n(int scene, float in_time, const float *cornell, const float *pts, const float *normals, float *out, int64_t n);
+void oracle_fresnel_conductor_n(const float *cosi, float eta, float k, float *out, int64_t n);
+void oracle_generate_ray(const float cam[12], float w, float h, int px, int py, int ortho, float out[6]);
+void oracle_ray_sphere_n(const float *origins, const float *dirs, float radius, float *out /*n·(hit,tmin,tmax)*/, int64_t n);
+void oracle_triplex_pow_n(const float *pts, float power, int power8, float *out, int64_t n);
+void oracle_de_triangle_n(const float *pts, const float tri[9], float *out, int64_t n);
+void oracle_smin_n(const float *a, const float *b, float k, float *out, int64_t n);
+/* GL cube sampler (conventions C4/C5) */
+void oracle_texture_cube(const oracle_frame *f, int slot, const float d[3], int nearest, float rgb[3]);
+int  oracle_quad_is_minified(int face_w, const float d[12]);
+
 /* HDREnvMap.hs / CoordTransf.hs / CornellBox.hs (oracle_envmap.c) */
 int  oracle_hdr_decode(const uint8_t *file, int64_t nbytes, int *w, int *h, float *rgb, int64_t cap_floats);
 int64_t oracle_hdr_encode(const float *rgb, int w, int h, uint8_t *out, int64_t cap);

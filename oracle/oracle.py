@@ -69,6 +69,17 @@ def lib():
         L.oracle_distance.argtypes = [C.c_int, C.c_float, fp, C.c_float, C.c_float, C.c_float]
         L.oracle_distance.restype = C.c_float
         L.oracle_glsl_eval.argtypes = [C.c_int, fp, fp, fp, C.c_int64]
+        i64 = C.c_int64
+        L.oracle_distance_n.argtypes = [C.c_int, C.c_float, fp, fp, fp, i64]
+        L.oracle_ray_march_n.argtypes = [C.c_int, C.c_float, fp, fp, fp, fp, i64]
+        L.oracle_normal_n.argtypes = [C.c_int, C.c_float, fp, C.c_int, fp, fp, i64]
+        L.oracle_distance_ao_n.argtypes = [C.c_int, C.c_float, fp, fp, fp, fp, i64]
+        L.oracle_fresnel_conductor_n.argtypes = [fp, C.c_float, C.c_float, fp, i64]
+        L.oracle_generate_ray.argtypes = [fp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, fp]
+        L.oracle_ray_sphere_n.argtypes = [fp, fp, C.c_float, fp, i64]
+        L.oracle_triplex_pow_n.argtypes = [fp, C.c_float, C.c_int, fp, i64]
+        L.oracle_de_triangle_n.argtypes = [fp, fp, fp, i64]
+        L.oracle_smin_n.argtypes = [fp, fp, C.c_float, fp, i64]
         L.oracle_hdr_decode.argtypes = [u8p, C.c_int64, ip, ip, fp, C.c_int64]; L.oracle_hdr_decode.restype = C.c_int
         L.oracle_hdr_encode.argtypes = [fp, C.c_int, C.c_int, u8p, C.c_int64]; L.oracle_hdr_encode.restype = C.c_int64
         L.oracle_rgbe_roundtrip.argtypes = [fp, C.c_int64, fp]
@@ -111,9 +122,66 @@ def camera(scene: int, time: float) -> np.ndarray:
 def distance(scene: int, time: float, pts: np.ndarray) -> np.ndarray:
     pts = _f32(pts).reshape(-1, 3)
     cv = cornell_vertices()
-    L = lib()
-    return np.array([L.oracle_distance(scene, C.c_float(time), _fp(cv), C.c_float(p[0]), C.c_float(p[1]), C.c_float(p[2]))
-                     for p in pts], np.float32)
+    out = np.empty(len(pts), np.float32)
+    lib().oracle_distance_n(scene, C.c_float(time), _fp(cv), _fp(pts), _fp(out), len(pts))
+    return out
+
+
+# single shader functions over arrays (lattice tests against oracle_ref)
+def ray_march(scene: int, time: float, origins, dirs) -> np.ndarray:
+    o = _f32(origins).reshape(-1, 3); d = _f32(dirs).reshape(-1, 3); cv = cornell_vertices()
+    out = np.empty((len(o), 2), np.float32)
+    lib().oracle_ray_march_n(scene, C.c_float(time), _fp(cv), _fp(o), _fp(d), _fp(out), len(o))
+    return out
+
+
+def normal(scene: int, time: float, pts, central: bool = False) -> np.ndarray:
+    pts = _f32(pts).reshape(-1, 3); cv = cornell_vertices(); out = np.empty_like(pts)
+    lib().oracle_normal_n(scene, C.c_float(time), _fp(cv), int(central), _fp(pts), _fp(out), len(pts))
+    return out
+
+
+def distance_ao(scene: int, time: float, pts, normals) -> np.ndarray:
+    pts = _f32(pts).reshape(-1, 3); nn = _f32(normals).reshape(-1, 3); cv = cornell_vertices()
+    out = np.empty(len(pts), np.float32)
+    lib().oracle_distance_ao_n(scene, C.c_float(time), _fp(cv), _fp(pts), _fp(nn), _fp(out), len(pts))
+    return out
+
+
+def fresnel_conductor(cosi, eta: float, k: float) -> np.ndarray:
+    c = _f32(cosi).ravel(); out = np.empty_like(c)
+    lib().oracle_fresnel_conductor_n(_fp(c), C.c_float(eta), C.c_float(k), _fp(out), c.size)
+    return out
+
+
+def generate_ray(cam, w: float, h: float, px: int, py: int, ortho: bool = False) -> np.ndarray:
+    c = _f32(cam); out = np.empty(6, np.float32)
+    lib().oracle_generate_ray(_fp(c), C.c_float(w), C.c_float(h), px, py, int(ortho), _fp(out))
+    return out
+
+
+def ray_sphere(origins, dirs, radius: float) -> np.ndarray:
+    o = _f32(origins).reshape(-1, 3); d = _f32(dirs).reshape(-1, 3); out = np.empty((len(o), 3), np.float32)
+    lib().oracle_ray_sphere_n(_fp(o), _fp(d), C.c_float(radius), _fp(out), len(o))
+    return out
+
+
+def triplex_pow(pts, power: float = 8.0, power8: bool = True) -> np.ndarray:
+    p = _f32(pts).reshape(-1, 3); out = np.empty_like(p)
+    lib().oracle_triplex_pow_n(_fp(p), C.c_float(power), int(power8), _fp(out), len(p))
+    return out
+
+
+def de_triangle(pts, tri) -> np.ndarray:
+    p = _f32(pts).reshape(-1, 3); t = _f32(tri).ravel(); out = np.empty(len(p), np.float32)
+    lib().oracle_de_triangle_n(_fp(p), _fp(t), _fp(out), len(p))
+    return out
+
+
+def smin(a, b, k: float) -> np.ndarray:
+    a = _f32(a).ravel(); b = _f32(b).ravel(); out = np.empty_like(a)
+    lib().oracle_smin_n(_fp(a), _fp(b), C.c_float(k), _fp(out), a.size)
+    return out
 
 
 def render(scene: int, fb_w: int, fb_h: int, time: float = 0.0, envs=None, rect=None,

@@ -42,6 +42,36 @@ def test_golden_frames(O):
             assert np.array_equal(O.render(s, 64, 64, t, envs=envs)["fb"], z["env_s%d_t%d" % (s, int(t))])
 
 
+def test_ref_golden_reference_shader_outputs(O):
+    """tests/golden/ref_shader.npz holds outputs of the reference's OWN fragment shader (compiled by g++
+    from /root/reference/fragment.shd, tests/golden/make_ref_golden.py): frames per shader variant (RGBA8
+    words, linear colour bits, hit masks), the commented-out shader switches, crops of BASELINE configs
+    1/3/4 at their real sizes and a distance-estimator lattice.  The C oracle must reproduce all of it."""
+    z = np.load(GOLD / "ref_shader.npz")
+    envs = _synthetic_envs(O)
+    for s in range(4):
+        for t in (0.0, 7.0):
+            for name, e in (("white", None), ("env", envs)):
+                r = O.render(s, 64, 48, t, envs=e)
+                k = "%s_s%d_t%d" % (name, s, int(t))
+                assert np.array_equal(r["fb"], z["fb_" + k]), k
+                lin, want = r["linear"].view(np.uint32), z["lin_" + k]
+                nan = np.isnan(r["linear"])
+                assert np.array_equal(nan, np.isnan(want.view(np.float32))) and np.array_equal(lin[~nan], want[~nan]), k
+                assert np.array_equal(np.packbits(r["hit"]), z["hit_" + k]), k
+    for s, fl in ((0, O.FLAG_RAY_TRACING_TEST), (1, O.FLAG_CAM_ORTHO), (2, O.FLAG_CAM_ORTHO)):
+        assert np.array_equal(O.render(s, 64, 48, 1.0, envs=envs, flags=fl)["fb"], z["fb_flag%d_s%d" % (fl, s)])
+    assert np.array_equal(O.render(2, 512, 512, 0.0, rect=(224, 240, 288, 272))["fb"], z["fb_c1_crop"])
+    assert np.array_equal(O.render(0, 3840, 2160, 0.0, rect=(1888, 1064, 1952, 1096))["fb"], z["fb_c3_cornell_crop"])
+    assert np.array_equal(O.render(1, 3840, 2160, 0.0, rect=(1888, 1064, 1952, 1096))["fb"], z["fb_c3_csg_crop"])
+    assert np.array_equal(O.render(2, 15360, 8640, 0.0, rect=(7648, 4304, 7712, 4336))["fb"], z["fb_c4_crop"])
+    pts = z["de_points"].view(np.float32)
+    for s in range(4):
+        got, want = O.distance(s, 7.0, pts), z["de_s%d" % s].view(np.float32)
+        nan = np.isnan(got)
+        assert np.array_equal(nan, np.isnan(want)) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32)), s
+
+
 def test_golden_julia_camera_cornell(O):
     z = np.load(GOLD / "julia_96x64.npz")
     for t in (0.0, 7.0, 123.5):
