@@ -168,14 +168,40 @@ class ClockSampler:
 
 
 # ---- CPU baseline (oracle; the only place bench.py touches oracle/) -----------------------
-def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12"))):
-    """Times the CPU restatement on a bounded, frame-covering sample of config 4: a 16×9 grid of
-    square crops spread uniformly over the 15360×8640 frame buffer, all host threads (OpenMP)."""
+def cpu_backend():
+    """The CPU implementation that is timed: oracle/_ref — the reference's OWN fragment.shd compiled by g++
+    (kind "reference") — when the prebuilt library is here, else the C restatement (kind "port").
+    Both take an explicit thread count (OpenMP num_threads clause), so torchrun's OMP_NUM_THREADS=1
+    does not apply."""
     from oracle import oracle as O
+    try:
+        from oracle import oracle_ref as REF
+        if REF.available():
+            return O, REF, "reference"
+    except Exception:
+        pass
+    return O, O, "port"
+
+
+def cpu_kind_note(kind: str) -> str:
+    return ("the reference's own fragment.shd compiled by g++ -O2 (oracle/_ref; GLSL built-ins = include/rmdf_glsl.h, LINEAR filtering — "
+            "the quad LOD rule would re-run NEAREST quads), OpenMP over rows of 2x2 quads; not llvmpipe (no GL in the image)" if kind == "reference"
+            else "C restatement of fragment.shd with OpenMP — not llvmpipe/GHC (absent from the image)")
+
+
+def oracle_env_cubes(O):
     img = O.hdr_decode((ROOT / "data" / "uffizi_512.hdr").read_bytes())
     small = O.resize(img, 256)
-    envs = [O.latlong_to_cube(img)] + [O.latlong_to_cube(O.rgbe_roundtrip(O.convolve(small, p))) for p in (1.0, 8.0, 64.0, 512.0)]
+    return [O.latlong_to_cube(img)] + [O.latlong_to_cube(O.rgbe_roundtrip(O.convolve(small, p))) for p in (1.0, 8.0, 64.0, 512.0)]
+
+
+def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12"))):
+    """Times the CPU implementation on a bounded, frame-covering sample of config 4: a 16×9 grid of
+    square crops spread uniformly over the 15360×8640 frame buffer, all host threads."""
+    O, B, kind = cpu_backend()
+    envs = oracle_env_cubes(O)
     cores = O.host_threads()
+    pol = O.LOD_ALWAYS_LINEAR if kind == "reference" else O.LOD_QUAD
 
     def run(crop):
         n, t0 = 0, time.perf_counter()
@@ -184,8 +210,9 @@ def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float
                 cx = (FB_W // 16) * gx + FB_W // 32
                 cy = (FB_H // 9) * gy + FB_H // 18
                 x0, y0 = (cx - crop // 2) & ~1, (cy - crop // 2) & ~1
-                r = O.render(SCENE_MB_POWER8, FB_W, FB_H, TIME, envs=envs, rect=(x0, y0, x0 + crop, y0 + crop), want_linear=False)
-                n += r["counters"]["samples"]
+                B.render(SCENE_MB_POWER8, FB_W, FB_H, TIME, envs=envs, rect=(x0, y0, x0 + crop, y0 + crop), want_linear=False,
+                         threads=cores, lod_policy=pol)
+                n += crop * crop
         return n, time.perf_counter() - t0
 
     n, dt = run(64)                                   # probe, then size the sample to the budget
@@ -198,22 +225,30 @@ def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float
         n, dt = run(crop)
         times.append(dt)
     dt = float(np.mean(times))
-    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "144 crops of %dx%d samples on a 16x9 grid over the 15360x8640 frame buffer (%.2f%% of the frame), "
-                      "C restatement of fragment.shd with OpenMP on all host threads — not llvmpipe/GHC (absent from the image)"
-                      % (crop, crop, 100.0 * n / (FB_W * FB_H)),
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": "144 crops of %dx%d samples on a 16x9 grid over the 15360x8640 frame buffer (%.2f%% of the frame); %s"
+                      % (crop, crop, 100.0 * n / (FB_W * FB_H), cpu_kind_note(kind)),
             "seconds_per_step": dt, "samples_per_step": n}
+
+
+def headline_config(mode_name: str, parallelism: str, l2: str) -> dict:
+    """`config` of the JSON line — the same keys and workload values on both arms."""
+    return {"workload": WORKLOAD, "scene": "FSMBPower8Shader", "in_time": TIME, "fb": [FB_W, FB_H], "out": [OUT_W, OUT_H],
+            "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": parallelism, "l2": l2}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    b = cpu_baseline_sample(steps=args.steps, warmup=min(args.warmup, 1))
+    # each step is a bounded sample sized so that the whole --steps/--warmup run ends within a few minutes
+    w = min(args.warmup, 1)
+    budget = max(0.3, min(float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12")), 150.0 / max(1, args.steps + w)))
+    b = cpu_baseline_sample(steps=args.steps, warmup=w, budget_s=budget)
     line = {"impl": "reference", "metric": "mandelbulb_4k_samples_per_s", "value": b["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": b["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference": "CPU oracle port (reference = Haskell+GLSL, unbuildable here)"},
+            "config": headline_config("cpu-" + b["kind"], "%d host threads (rank 0 only)" % b["cores"], "n/a (CPU)"),
             "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": b["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -356,7 +391,7 @@ def run_ours(args):
     c = sr.counters()
     launches = (c["launches"] - l0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1)
+    ms_e2e = timed(step_e2e, args.steps, 2)
     e2e_same = None
     if host_shared is not None:                       # the host frame the e2e path produced == the device-resident frame
         step_resident(); step_e2e(); barrier()
@@ -406,9 +441,8 @@ def run_ours(args):
             "metric": "mandelbulb_4k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "scene": "FSMBPower8Shader", "in_time": TIME, "fb": [FB_W, FB_H], "out": [OUT_W, OUT_H],
-                       "spp": 1 << (2 * SPP_LOG2), "mode": mode_name, "parallelism": ("tiles %dx%d, rank = (tx + %d*ty) mod %d, %s" % (grid[0], grid[1], skew, world, "tile stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if sharded else "single GPU",
-                       "l2": "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"},
+            "config": headline_config(mode_name, ("tiles %dx%d, rank = (tx + %d*ty) mod %d, %s" % (grid[0], grid[1], skew, world, "tile stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if sharded else "single GPU",
+                                      "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"),
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4,
                     "path": ("rmdf_render with a page-locked host frame buffer: the kernel's stores are the D2H" if not sharded else
@@ -432,6 +466,10 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             b = cpu_baseline_sample()
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not args.no_configs:
+            # the other BASELINE configs (1, 2, 3, 5) and the fourth scene, a few hundred ms of GPU time in all
+            import bench_configs
+            line["configs"] = bench_configs.measure(sr, cubes, torch, R, flush, local, stream, with_cpu=not args.no_cpu_baseline)
         emit(line)
     if host_shared is not None:
         host_shared.close()
@@ -452,25 +490,30 @@ F_JULIA_ITER = 13.0                                                # flop per it
 
 
 def julia_cpu_baseline(steps: int = 1, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12"))):
-    """The CPU restatement of Fractal2D.hs on all host threads over 135 row slabs spread uniformly
-    over the 34560 rows (forSegmentsConcurrently-style row split inside each slab)."""
+    """The CPU restatement of Fractal2D.hs over 135 row slabs spread uniformly over the 34560 rows, each slab
+    split the reference's way: makeNSegments into one contiguous row segment per host thread
+    (forSegmentsConcurrently Nothing, Fractal2D.hs:98 / ConcurrentSegments.hs:14-28)."""
     from oracle import oracle as O
+    cores = O.host_threads()
+    unit = max(32, cores)                              # at least one row per segment
+
     def run(rows_per_slab):
         n, t0 = 0, time.perf_counter()
         for i in range(135):
             y0 = i * 256
-            O.julia(J_FB_W, J_FB_H, False, J_TICK, rows=(y0, y0 + rows_per_slab))
+            O.julia(J_FB_W, J_FB_H, False, J_TICK, rows=(y0, y0 + rows_per_slab), segments=cores)
             n += rows_per_slab * J_FB_W
         return n, time.perf_counter() - t0
-    n, dt = run(32)                                   # probe (32 rows keep every host thread busy)
-    rows = int(max(32, min(256, (n / dt) * budget_s / (135 * J_FB_W))))
+    n, dt = run(unit)                                  # probe
+    rows = int(max(unit, min(256, (n / dt) * budget_s / (135 * J_FB_W))))
     times = []
     for _ in range(max(1, steps)):
         n, dt = run(rows); times.append(dt)
     dt = float(np.mean(times))
-    return {"value": n / dt, "unit": "samples/s", "cores": O.host_threads(), "kind": "port",
-            "sample": "135 slabs of %d rows x 61440 samples spread over the frame (%.2f%% of it), C restatement of Fractal2D.hs with OpenMP — not GHC"
-                      % (rows, 100.0 * n / (J_FB_W * J_FB_H)), "seconds_per_step": dt}
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "135 slabs of %d rows x 61440 samples spread over the frame (%.2f%% of it), each cut by makeNSegments into %d row segments, one thread each "
+                      "(the reference's forSegmentsConcurrently); C restatement of Fractal2D.hs — not GHC" % (rows, 100.0 * n / (J_FB_W * J_FB_H), cores),
+            "seconds_per_step": dt}
 
 
 def run_julia(args):
@@ -558,7 +601,7 @@ def run_julia(args):
     ms_res = timed(step_resident, args.steps, args.warmup, True)
     c = sr.counters()
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, max(2, min(args.steps, 5)), 1, False)
+    ms_e2e = timed(step_e2e, args.steps, 2, False)
     its = torch.tensor([c["inner_iters"] / (args.steps + args.warmup)], dtype=torch.float64, device=dev)
     kt = torch.tensor([c["last_kernel_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -599,6 +642,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "parity", "fast"],
                     help="auto: the fast build if it meets BASELINE's tolerance against the parity build in this run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs (N = 1 only)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-memory stores (default) or NCCL gather")
     ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
                     help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")

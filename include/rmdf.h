@@ -228,6 +228,9 @@ int  rmdf_counters_reset(rmdf_ctx *ctx);
 /* FP32 FMA roofline denominator: an FFMA-chain microbenchmark on ctx's device (the
  * reference has no counterpart).  tflops = 2·FFMA/s, sm_mhz = SM clock sustained. */
 int  rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz);
+/* MUFU (XU pipe) roofline denominator for the transcendental-bound scenes: ex2.approx chains;
+ * gops = 1e9 MUFU lane-operations per second (16 lanes/clk/SM on sm_100a). */
+int  rmdf_measure_mufu_peak(rmdf_ctx *ctx, float *gops);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,8 @@ void oracle_rgbe_roundtrip(const float *rgb, int64_t npix, float *out);
 int  oracle_resize_height(int srcw, int srch, int dstw);
 void oracle_resize(const float *src, int srcw, int srch, int dstw, float *dst);
 void oracle_convolve(const float *src, int w, int h, float power, float *dst, int threads);
+void oracle_convolve_rows(const float *src, int w, int h, float power, float *dst, int y0, int y1, int threads);
+void oracle_convolve_sweep_rows(const float *src, int w, int h, const float *powers, int np, float *dst, int y0, int y1);
 void oracle_latlong_to_cube(const float *latlong, int w, int h, float *faces /*6·fw·fw·3*/, int round_half);
 void oracle_cube_pixel_to_dir(int face, int w, int x, int y, float dir[3]);
 void oracle_test_latlong_envmap(float *rgb /*512·256·3*/);
@@ -73,6 +75,7 @@ int  oracle_make_segments(int nseg, int low, int high, int *out_pairs, int cap_p
 
 /* Fractal2D.hs (oracle_julia.c) */
 void oracle_julia(int w, int h, uint32_t *fb, int smooth, double tick, int y0, int y1, int threads);
+void oracle_julia_segments(int w, int h, uint32_t *fb, int smooth, double tick, int y0, int y1, int nseg);
 
 /* FrameBuffer.hs mip resolve + screenshot orientation (oracle_fb.c) */
 void oracle_mip_resolve(const uint32_t *fb, int w, int h, int levels, uint32_t *out);

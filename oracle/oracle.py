@@ -86,6 +86,9 @@ def lib():
         L.oracle_resize_height.argtypes = [C.c_int] * 3; L.oracle_resize_height.restype = C.c_int
         L.oracle_resize.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp]
         L.oracle_convolve.argtypes = [fp, C.c_int, C.c_int, C.c_float, fp, C.c_int]
+        L.oracle_convolve_rows.argtypes = [fp, C.c_int, C.c_int, C.c_float, fp, C.c_int, C.c_int, C.c_int]
+        L.oracle_convolve_sweep_rows.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int]
+        L.oracle_julia_segments.argtypes = [C.c_int, C.c_int, u32p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
         L.oracle_latlong_to_cube.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int]
         L.oracle_cube_pixel_to_dir.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, fp]
         L.oracle_test_latlong_envmap.argtypes = [fp]
@@ -282,6 +285,25 @@ def convolve(img: np.ndarray, power: float, threads: int = 0) -> np.ndarray:
     return out
 
 
+def convolve_rows(img: np.ndarray, power: float, rows, threads: int = 0) -> np.ndarray:
+    """destination rows [y0, y1) only; returns those rows"""
+    img = _f32(img)
+    h, w, _ = img.shape
+    out = np.zeros_like(img)
+    lib().oracle_convolve_rows(_fp(img), w, h, C.c_float(power), _fp(out), rows[0], rows[1], threads)
+    return out[rows[0]:rows[1]]
+
+
+def convolve_sweep_rows(img: np.ndarray, powers, rows) -> np.ndarray:
+    """The reference's decomposition (ShaderRendering.hs:142): one thread per power, each sequential."""
+    img = _f32(img)
+    h, w, _ = img.shape
+    pw = _f32(list(powers))
+    out = np.zeros((len(pw),) + img.shape, np.float32)
+    lib().oracle_convolve_sweep_rows(_fp(img), w, h, _fp(pw), len(pw), _fp(out), rows[0], rows[1])
+    return out[:, rows[0]:rows[1]]
+
+
 def latlong_to_cube(img: np.ndarray, round_half: bool = True) -> np.ndarray:
     img = _f32(img)
     h, w, _ = img.shape
@@ -311,12 +333,17 @@ def make_segments(nseg: int, low: int, high: int):
 
 
 # ---------------------------------------------------------------- julia / frame buffer
-def julia(w: int, h: int, smooth: bool, tick: float, rows=None, threads: int = 0) -> np.ndarray:
+def julia(w: int, h: int, smooth: bool, tick: float, rows=None, threads: int = 0, segments: int = 0) -> np.ndarray:
+    """segments > 0: the reference's forSegmentsConcurrently decomposition (Fractal2D.hs:98) — the rows cut
+    by makeNSegments into `segments` contiguous bands, one thread each; else OpenMP dynamic over rows."""
     y0, y1 = rows if rows is not None else (0, h)
     fb = np.zeros((y1 - y0, w), np.uint32)
     # the C function indexes px + py·w with absolute py: hand it the address row 0 would have
     base = C.cast(C.c_void_p(fb.ctypes.data - y0 * w * 4), C.POINTER(C.c_uint32))
-    lib().oracle_julia(w, h, base, int(smooth), C.c_double(tick), y0, y1, threads)
+    if segments > 0:
+        lib().oracle_julia_segments(w, h, base, int(smooth), C.c_double(tick), y0, y1, segments)
+    else:
+        lib().oracle_julia(w, h, base, int(smooth), C.c_double(tick), y0, y1, threads)
     return fb
 
 
@@ -337,4 +364,9 @@ def screenshot_rows(fb: np.ndarray) -> np.ndarray:
 
 
 def host_threads() -> int:
-    return os.cpu_count() or 1
+    """The threads the CPU legs really use: the oracle's `threads` argument is always passed explicitly
+    (num_threads clause), so OMP_NUM_THREADS — which torchrun sets to 1 — does not apply."""
+    try:
+        return len(os.sched_getaffinity(0)) or 1
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1

@@ -191,14 +191,15 @@ void oracle_resize(const float *src, int srcw, int srch, int dstw, float *dst)
 }
 
 /* ---- HDREnvMap.hs:217-254  O(n^4) cosine-power convolution -------------------- */
-void oracle_convolve(const float *src, int srcw, int srch, float power, float *dst, int threads)
+/* destination rows [y0,y1) only (the CPU-baseline sample of bench.py); dst is a full-size image */
+void oracle_convolve_rows(const float *src, int srcw, int srch, float power, float *dst, int y0, int y1, int threads)
 {
     int dsty;
     (void)threads;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : omp_get_max_threads())
 #endif
-    for (dsty = 0; dsty < srch; dsty++) {
+    for (dsty = y0; dsty < y1; dsty++) {
         float *lookup = (float *)malloc(sizeof(float) * (size_t)srcw);
         int dstx, x, y;
         for (dstx = 0; dstx < srcw; dstx++) {
@@ -229,6 +230,21 @@ void oracle_convolve(const float *src, int srcw, int srch, float power, float *d
         }
         free(lookup);
     }
+}
+void oracle_convolve(const float *src, int srcw, int srch, float power, float *dst, int threads)
+{
+    oracle_convolve_rows(src, srcw, srch, power, dst, 0, srch, threads);
+}
+/* The reference's own decomposition of the sweep (ShaderRendering.hs:142 `mapConcurrently` over the
+ * powers, each cosineConvolveHDREnvMap sequential): one thread per power; rows [y0,y1) of every image. */
+void oracle_convolve_sweep_rows(const float *src, int srcw, int srch, const float *powers, int np, float *dst, int y0, int y1)
+{
+    int k;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(np)
+#endif
+    for (k = 0; k < np; k++)
+        oracle_convolve_rows(src, srcw, srch, powers[k], dst + (size_t)k * srcw * srch * 3, y0, y1, 1);
 }
 
 /* ---- linear's normalize (see header) ------------------------------------------ */

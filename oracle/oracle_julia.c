@@ -43,7 +43,7 @@ void oracle_julia(int w, int h, uint32_t *fb, int smooth, double tick, int y0, i
     int py;
     (void)threads;
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 4) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads > 0 ? threads : omp_get_max_threads()) if (threads != 1)
 #endif
     for (py = y0; py < y1; py++) {
         int px;
@@ -72,4 +72,20 @@ void oracle_julia(int w, int h, uint32_t *fb, int smooth, double tick, int y0, i
             fb[(size_t)px + (size_t)py * (size_t)w] = ((uint32_t)(int32_t)truncf(val)) << 8;
         }
     }
+}
+
+/* Fractal2D.hs:98 `forSegmentsConcurrently Nothing 0 h`: rows [y0,y1) cut by makeNSegments
+ * (ConcurrentSegments.hs:14-23) into nseg contiguous segments, one thread per segment — the
+ * reference's own thread decomposition (nseg defaults to the processor count there). */
+void oracle_julia_segments(int w, int h, uint32_t *fb, int smooth, double tick, int y0, int y1, int nseg)
+{
+    int pairs[2 * 1024], n, i;
+    if (nseg < 1) nseg = 1;
+    if (nseg > 1024) nseg = 1024;
+    n = oracle_make_segments(nseg, y0, y1, pairs, 1024);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(n > 0 ? n : 1)
+#endif
+    for (i = 0; i < n; i++)
+        oracle_julia(w, h, fb, smooth, tick, pairs[2 * i], pairs[2 * i + 1], 1);
 }

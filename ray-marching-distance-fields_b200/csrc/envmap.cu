@@ -199,7 +199,9 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
 __device__ __forceinline__ void pixel_at_bilinear(const float *img, int w, int h, float u, float v, float out[3])
 {
     const float upx = u * ((float)w - 1.0f), upy = v * ((float)h - 1.0f);
-    const int x = (int)floorf(upx), y = (int)floorf(upy);
+    // The reference indexes with unsafePixelAt and can read one row past the image when dsth rounds up
+    // (e.g. 200×103 → 100×52); a C ABI taking arbitrary sizes clamps instead — identical for every in-range sample.
+    const int x = min(max((int)floorf(upx), 0), w - 1), y = min(max((int)floorf(upy), 0), h - 1);
     const int xp1 = (x + 1) % (w - 1);                       // sic: mod (w-1), :100
     const int yp1 = min(h - 1, y + 1);
     const float ur = upx - (float)x, vr = upy - (float)y, uo = 1.0f - ur, vo = 1.0f - vr;

@@ -55,4 +55,46 @@ cudaError_t measure_fp32_peak(int sm_count, cudaStream_t s, float *tflops, float
     return e;
 }
 
+// MUFU (XU pipe) roofline denominator for the transcendental-bound scenes (general-power Mandelbulb,
+// CSG test scene): four independent ex2.approx chains per thread.  sm_100a issues one MUFU warp
+// instruction per 8 cycles per SM sub-partition = 16 lanes/clk/SM (profiles/experiments/mufu_bench.cu:
+// rsq, ex2, lg2, sqrt and sin all measure the same 8.04 cycles).
+__global__ void __launch_bounds__(256)
+mufu_peak_kernel(float *sink, int iters)
+{
+    float f0 = 1.0f + threadIdx.x * 1e-3f, f1 = f0 + 1.f, f2 = f0 + 2.f, f3 = f0 + 3.f;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f0));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f1));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f2));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f3));
+        }
+    }
+    const float s = (f0 + f1) + (f2 + f3);
+    if (s == 123.456f) sink[0] = s;
+}
+
+cudaError_t measure_mufu_peak(int sm_count, cudaStream_t s, float *gops)
+{
+    float *sink = nullptr;
+    cudaError_t e = cudaMalloc(&sink, 4); if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = sm_count * 8, iters = 1024;
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, s);
+        mufu_peak_kernel<<<grid, 256, 0, s>>>(sink, iters);
+        cudaEventRecord(e1, s);
+        e = cudaStreamSynchronize(s); if (e != cudaSuccess) break;
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best_ms) best_ms = ms;
+    }
+    if (e == cudaSuccess) *gops = (float)(4.0 * 16.0 * (double)iters * 256.0 * (double)grid / (best_ms * 1e-3) / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return e;
+}
+
 }  // namespace rmdf

@@ -60,12 +60,23 @@ struct rmdf_ctx {
     std::recursive_mutex mu;
 };
 
-static int use(rmdf_ctx *ctx)
-{
-    if (!ctx) return fail(RMDF_ERR_ARG, "ctx is NULL");
-    CU(cudaSetDevice(ctx->device));
-    return RMDF_OK;
-}
+// Every entry point runs on ctx's device and puts the caller's current device back on return: a host
+// with several GPUs in one process (or torch, which reads cudaGetDevice) must not see it change.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    int enter(rmdf_ctx *ctx)
+    {
+        if (!ctx) return fail(RMDF_ERR_ARG, "ctx is NULL");
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != ctx->device) {
+            CU(cudaSetDevice(ctx->device));
+            changed = true;
+        }
+        return RMDF_OK;
+    }
+    ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+};
 static int ensure_staging(rmdf_ctx *ctx, size_t bytes)
 {
     if (ctx->d_out_bytes >= bytes) return RMDF_OK;
@@ -88,6 +99,8 @@ extern "C" int rmdf_create(rmdf_ctx **out, int device)
     if (e != cudaSuccess || ndev == 0)
         return fail(RMDF_ERR_CUDA, "no CUDA device: %s (librmdf_b200 has no CPU fallback)", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(RMDF_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+    struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+    if (cudaGetDevice(&restore.prev) != cudaSuccess) { cudaGetLastError(); restore.prev = -1; }
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -128,6 +141,8 @@ static void free_slot(EnvSlot &s)
 extern "C" void rmdf_destroy(rmdf_ctx *ctx)
 {
     if (!ctx) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < RMDF_ENV_SLOTS; i++) free_slot(ctx->env[i]);
@@ -139,11 +154,12 @@ extern "C" void rmdf_destroy(rmdf_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 extern "C" int rmdf_set_stream(rmdf_ctx *ctx, void *cuda_stream)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
@@ -151,7 +167,7 @@ extern "C" int rmdf_set_stream(rmdf_ctx *ctx, void *cuda_stream)
 }
 extern "C" int rmdf_sync(rmdf_ctx *ctx)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     return RMDF_OK;
 }
@@ -165,7 +181,7 @@ extern "C" int rmdf_envmap_resize_height(int w, int h, int dstw)
 
 extern "C" int rmdf_envmap_resize(rmdf_ctx *ctx, const float *rgb, int w, int h, int dstw, float *out)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!rgb || !out || w < 2 || h < 2 || dstw < 1) return fail(RMDF_ERR_ARG, "rmdf_envmap_resize: bad image %dx%d -> %d", w, h, dstw);
     const int dsth = rmdf_envmap_resize_height(w, h, dstw);
     if (dsth < 1) return fail(RMDF_ERR_ARG, "rmdf_envmap_resize: target height is 0");
@@ -193,7 +209,7 @@ static int convolve_check(const void *rgb, int w, int h, const float *powers, in
 extern "C" int rmdf_envmap_convolve_rows_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
                                                 const float *powers, int np, int row_begin, int row_end, void *out_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if ((rc = convolve_check(rgb_dev, w, h, powers, np, out_dev))) return rc;
     if (row_begin < 0 || row_end > h || row_begin >= row_end) return fail(RMDF_ERR_ARG, "rmdf_envmap_convolve: rows [%d,%d) outside [0,%d)", row_begin, row_end, h);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -213,7 +229,7 @@ extern "C" int rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, i
 extern "C" int rmdf_envmap_convolve(rmdf_ctx *ctx, const float *rgb, int w, int h,
                                     const float *powers, int np, float *out)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if ((rc = convolve_check(rgb, w, h, powers, np, out))) return rc;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     float *d_src = nullptr, *d_dst = nullptr;
@@ -306,7 +322,7 @@ static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *fa
 
 extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     if (!faces_rgb || face_w < 1 || face_w > 8192) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind_cube: bad faces (w = %d)", face_w);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -328,7 +344,7 @@ extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces
 
 extern "C" int rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rgb, int w, int h)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     if (!latlong_rgb || w < 3 || h < 2) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind: bad image %dx%d", w, h);
     const int fw = w / 3;                                    // HDREnvMap.hs:128
@@ -354,7 +370,7 @@ extern "C" int rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rg
 
 extern "C" int rmdf_envmap_get_cube(rmdf_ctx *ctx, int slot, float *faces_rgb, int *face_w)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     const EnvSlot &s = ctx->env[slot];
@@ -368,7 +384,7 @@ extern "C" int rmdf_envmap_get_cube(rmdf_ctx *ctx, int slot, float *faces_rgb, i
 
 extern "C" int rmdf_envmap_unbind(rmdf_ctx *ctx, int slot)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -415,7 +431,7 @@ extern "C" int rmdf_cornell_box_vertices(float *xyz)
 
 extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!xyz || nverts != 96) return fail(RMDF_ERR_ARG, "rmdf_set_cornell: expected 96 vertices, got %d", nverts);
     // position-independent terms of compute_barycentric / line_seg_min_dist_sq
     // (fragment.shd:312-346), same operation order as the shader
@@ -582,13 +598,13 @@ static int pick_item_h(int64_t blocks_of_32_rows, int resident_warps, int k)
 
 extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     WorkList wl;
     if ((rc = build_worklist(p, &wl))) return rc;
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if ((p->scene == RMDF_SCENE_CORNELL_BOX || (p->flags & RMDF_FLAG_RAY_TRACING_TEST)) && !ctx->have_cornell)
         return fail(RMDF_ERR_STATE, "Cornell scene requested before rmdf_set_cornell");
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
 
     MarchParams mp;
     memset(&mp, 0, sizeof mp);
@@ -671,7 +687,7 @@ static void *device_view_of_host(const void *host)
 
 extern "C" int rmdf_render(rmdf_ctx *ctx, const rmdf_params *p, void *fb_host)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     WorkList wl;
     if ((rc = build_worklist(p, &wl))) return rc;
     if (!fb_host) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
@@ -758,7 +774,7 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
 extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
                                  int y0, int y1, int resolve_log2, void *fb_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
     JuliaParams jp;
     if ((rc = julia_params(ctx, w, h, smooth, tick, y0, y1, resolve_log2, 0, 0, 1, &jp))) return rc;
@@ -768,7 +784,7 @@ extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double
 extern "C" int rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, double tick, int resolve_log2,
                                        int band_h, int shard_rank, int shard_count, int layout, void *fb_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
     if (layout != RMDF_LAYOUT_FRAME && layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", layout);
     JuliaParams jp;
@@ -780,7 +796,7 @@ extern "C" int rmdf_julia_bands_device(rmdf_ctx *ctx, int w, int h, int smooth, 
 extern "C" int rmdf_julia(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
                           int y0, int y1, int resolve_log2, uint32_t *fb_host)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!fb_host) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
     if (resolve_log2 < 0 || resolve_log2 > 3 || y1 <= y0 || w < 1) return fail(RMDF_ERR_ARG, "rmdf_julia: bad arguments");
     const size_t bytes = sizeof(uint32_t) * (size_t)(w >> resolve_log2) * (size_t)((y1 - y0) >> resolve_log2);
@@ -797,7 +813,7 @@ extern "C" int rmdf_julia(rmdf_ctx *ctx, int w, int h, int smooth, double tick,
 // ---- frame-buffer helpers ----------------------------------------------------------------
 extern "C" int rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w, int h, int levels, void *out_dev)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!fb_dev || !out_dev || w < 1 || h < 1 || levels < 0 || levels > 16 || (w >> levels) < 1 || (h >> levels) < 1)
         return fail(RMDF_ERR_ARG, "rmdf_mip_resolve_device: bad arguments");
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -810,7 +826,7 @@ extern "C" int rmdf_mip_resolve_device(rmdf_ctx *ctx, const void *fb_dev, int w,
 // ---- multi-GPU shared frame buffer ------------------------------------------------------------
 extern "C" int rmdf_shared_alloc(rmdf_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char handle[64])
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!dev_ptr || !handle || bytes <= 0) return fail(RMDF_ERR_ARG, "rmdf_shared_alloc: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     void *p = nullptr;
@@ -824,14 +840,15 @@ extern "C" int rmdf_shared_alloc(rmdf_ctx *ctx, int64_t bytes, void **dev_ptr, u
 }
 extern "C" int rmdf_shared_free(rmdf_ctx *ctx, void *dev_ptr)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFree(dev_ptr));
     return RMDF_OK;
 }
 extern "C" int rmdf_shared_open(rmdf_ctx *ctx, const unsigned char handle[64], void **dev_ptr)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!dev_ptr || !handle) return fail(RMDF_ERR_ARG, "rmdf_shared_open: bad arguments");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
@@ -840,14 +857,15 @@ extern "C" int rmdf_shared_open(rmdf_ctx *ctx, const unsigned char handle[64], v
 }
 extern "C" int rmdf_shared_close(rmdf_ctx *ctx, void *dev_ptr)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaIpcCloseMemHandle(dev_ptr));
     return RMDF_OK;
 }
 extern "C" int rmdf_enable_peer(rmdf_ctx *ctx, int peer_device)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     int can = 0;
     CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
     if (!can) return fail(RMDF_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer_device);
@@ -859,7 +877,7 @@ extern "C" int rmdf_enable_peer(rmdf_ctx *ctx, int peer_device)
 
 extern "C" int rmdf_host_register(rmdf_ctx *ctx, void *host_ptr, int64_t bytes, void **dev_ptr)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!host_ptr || !dev_ptr || bytes <= 0) return fail(RMDF_ERR_ARG, "rmdf_host_register: bad arguments");
     cudaError_t e = cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(RMDF_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
@@ -869,7 +887,7 @@ extern "C" int rmdf_host_register(rmdf_ctx *ctx, void *host_ptr, int64_t bytes, 
 }
 extern "C" int rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!host_ptr) return fail(RMDF_ERR_ARG, "rmdf_host_unregister: NULL");
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaHostUnregister(host_ptr));
@@ -879,7 +897,7 @@ extern "C" int rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr)
 // ---- measurement ----------------------------------------------------------------------------
 extern "C" int rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mhz)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!tflops || !sm_mhz) return fail(RMDF_ERR_ARG, "rmdf_measure_fp32_peak: NULL");
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaError_t e = measure_fp32_peak(ctx->sm_count, ctx->stream, tflops, sm_mhz);
@@ -888,10 +906,21 @@ extern "C" int rmdf_measure_fp32_peak(rmdf_ctx *ctx, float *tflops, float *sm_mh
     return RMDF_OK;
 }
 
+extern "C" int rmdf_measure_mufu_peak(rmdf_ctx *ctx, float *gops)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!gops) return fail(RMDF_ERR_ARG, "rmdf_measure_mufu_peak: NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaError_t e = measure_mufu_peak(ctx->sm_count, ctx->stream, gops);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_measure_mufu_peak: %s", cudaGetErrorString(e));
+    ctx->launches += 5;
+    return RMDF_OK;
+}
+
 // ---- counters -----------------------------------------------------------------------------
 extern "C" int rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!out) return fail(RMDF_ERR_ARG, "out is NULL");
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     unsigned long long h[C_NSLOTS];
@@ -909,7 +938,7 @@ extern "C" int rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out)
 }
 extern "C" int rmdf_counters_reset(rmdf_ctx *ctx)
 {
-    int rc = use(ctx); if (rc) return rc;
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS, ctx->stream));
     return RMDF_OK;

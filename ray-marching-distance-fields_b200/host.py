@@ -415,6 +415,12 @@ class ShaderRenderer:
         check(self._lib.rmdf_measure_fp32_peak(self._h, C.byref(t), C.byref(f)))
         return {"tflops": float(t.value), "sm_mhz": float(f.value)}
 
+    def measureMufuPeak(self) -> float:
+        """1e9 MUFU lane-operations per second (the XU-pipe roofline denominator)."""
+        g = C.c_float(0)
+        check(self._lib.rmdf_measure_mufu_peak(self._h, C.byref(g)))
+        return float(g.value)
+
     def resetCounters(self) -> None:
         check(self._lib.rmdf_counters_reset(self._h))
 

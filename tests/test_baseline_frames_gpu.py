@@ -81,25 +81,36 @@ def test_config4_crops_15360x8640(sr, O, R, oracle_envs):
 
 def test_config4_fast_build_tolerance_on_oracle_crops(sr, O, R, oracle_envs):
     """BASELINE's bar for the fast build at config 4's sampling rate, AGAINST THE ORACLE (not the parity
-    build): level-0 FP32 crops of the real 15360×8640 frame, 4×4 box in linear RGB, hit masks."""
+    build): hit masks agree on >= 99.9 % of samples and linear-RGB PSNR >= 50 dB on the 16-spp resolved
+    image.  The bar is stated on the frame, so the estimate uses a UNIFORM sample of it: a 16×8 grid of
+    128×64-sample crops (two per tile of the reference's 8×8 grid), level-0 FP32 colour of the real
+    15360×8640 frame, 4×4 box in linear RGB clamped to [0,1].  The figure over the crops that contain
+    geometry only is printed beside it (harsher: no background pixels to dilute the error)."""
     _bind(sr, oracle_envs)
     fb_w, fb_h, s = 15360, 8640, 4
     tw, th = fb_w // 8, fb_h // 8
-    se, n, agree, cnt = 0.0, 0, 0.0, 0
-    for idx in (27, 28, 35, 36):                      # the four centre tiles of the reference's 8×8 grid
+    cw, ch = 128, 64
+    box = lambda a: np.clip(np.nan_to_num(a), 0, 1).reshape(ch // s, s, cw // s, s, 3).mean(axis=(1, 3))
+    se = n = se_g = n_g = 0.0
+    agree, cnt = 0.0, 0
+    for idx in range(64):
         fast = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, idx, fb_w, fb_h, 0.0, out_format=R.OUT_RGBA32F,
                                  mode=R.MODE_FAST, layout=R.LAYOUT_PACKED_TILES).reshape(th, tw, 4)
         tx, ty = idx % 8, idx // 8
-        for (cx, cy) in ((0, 0), (tw - 256, th - 128), (tw // 2, th // 2), (640, 200)):
-            rect = (tx * tw + cx, ty * th + cy, tx * tw + cx + 256, ty * th + cy + 128)
+        for cx in (tw // 4 - cw // 2, 3 * tw // 4 - cw // 2):
+            cy = th // 2 - ch // 2
+            rect = (tx * tw + cx, ty * th + cy, tx * tw + cx + cw, ty * th + cy + ch)
             ref = O.render(2, fb_w, fb_h, 0.0, envs=oracle_envs, rect=rect)
-            f = fast[cy:cy + 128, cx:cx + 256]
-            box = lambda a: np.clip(np.nan_to_num(a), 0, 1).reshape(128 // s, s, 256 // s, s, 3).mean(axis=(1, 3))
+            f = fast[cy:cy + ch, cx:cx + cw]
             d = box(f[..., :3]).astype(np.float64) - box(ref["linear"]).astype(np.float64)
             se += float((d ** 2).sum()); n += d.size
+            if ref["hit"].any():
+                se_g += float((d ** 2).sum()); n_g += d.size
             agree += float(np.mean((f[..., 3] > 0.5) == ref["hit"].astype(bool))); cnt += 1
     p = float("inf") if se == 0 else 10 * np.log10(n / se)
-    print("config 4 fast build vs oracle, 16 crops of 256x128 samples: hit agreement %.5f%%, linear PSNR %.2f dB" % (100 * agree / cnt, p))
+    pg = float("inf") if se_g == 0 else 10 * np.log10(n_g / se_g)
+    print("config 4 fast build vs oracle, 128 uniform crops of 128x64 samples: hit agreement %.5f%%, linear PSNR %.2f dB "
+          "(crops with geometry only: %.2f dB over %d of %d output pixels)" % (100 * agree / cnt, p, pg, n_g // 3, n // 3))
     assert agree / cnt >= 0.999 and p >= 50.0
 
 

@@ -237,11 +237,38 @@ def test_gather_frame_gloo_world_size_2(tmp_path):
 def test_bench_reference_arm_contract():
     """--impl reference prints one JSON line with the contract's keys (tiny budget)."""
     import json
-    env = dict(os.environ, RMDF_BENCH_CPU_BUDGET_S="0.5")
+    # OMP_NUM_THREADS=1 is what torch.distributed.run exports when nproc > 1: the CPU legs pass their thread
+    # count explicitly, so it must not apply (round 1's reference arm ran single-threaded under torchrun)
+    env = dict(os.environ, RMDF_BENCH_CPU_BUDGET_S="0.5", OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import oracle_ref
+    assert line["cpu_baseline"]["kind"] == ("reference" if oracle_ref.available() else "port")
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # same workload keys as the GPU arm's config
+    for k, v in (("scene", "FSMBPower8Shader"), ("in_time", 0.0), ("fb", [15360, 8640]), ("out", [3840, 2160]), ("spp", 16)):
+        assert line["config"][k] == v
+    # rank != 0 of a torchrun launch exits 0 without printing
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_threads_are_real(O):
+    """The thread count the CPU legs report is the one OpenMP uses, whatever OMP_NUM_THREADS says: the same crop
+    rendered with threads=1 and threads=all must show a speed-up when more than one core is available."""
+    import time
+    cores = O.host_threads()
+    if cores < 4:
+        pytest.skip("needs >= 4 host threads")
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        t0 = time.perf_counter(); O.render(2, 512, 512, 0.0, threads=1, want_linear=False); t1 = time.perf_counter() - t0
+        t0 = time.perf_counter(); O.render(2, 512, 512, 0.0, threads=cores, want_linear=False); tn = time.perf_counter() - t0
+    finally:
+        os.environ.pop("OMP_NUM_THREADS", None)
+    assert tn < t1 / 1.8, (t1, tn, cores)
