@@ -126,7 +126,8 @@ def tolerance_check(sr, torch, R):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms while the timed region runs (the profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
@@ -136,19 +137,23 @@ class ClockSampler:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
-            pass
+            return
+        t0 = time.perf_counter()                      # nvidia-smi needs a few hundred ms to print its first row
+        while time.perf_counter() - t0 < 3.0 and os.path.getsize(self.f.name) == 0 and self.p.poll() is None:
+            time.sleep(0.02)
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        time.sleep(0.06)                              # one more sampling period
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush(); self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
+        sm, mx, reasons, power, busy = [], [], set(), [], []
         for line in self.f.read().splitlines():
             t = [x.strip() for x in line.split(",")]
             if len(t) < 9:
@@ -157,13 +162,18 @@ class ClockSampler:
                 sm.append(float(t[1])); mx.append(float(t[2])); power.append(float(t[3]))
             except ValueError:
                 continue
+            try:
+                busy.append(float(t[4]) > 0.0)
+            except ValueError:
+                busy.append(False)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.f.name)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "power_w_max": float(max(power)), "samples": len(sm)}
+            load = [c for c, b in zip(sm, busy) if b] or sm
+            out = {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "power_w_max": float(max(power)), "samples": len(sm), "samples_under_load": int(sum(busy))}
         return out
 
 

@@ -196,7 +196,7 @@ def test_cuda_equals_reference_shader_live(sr, O, R, oracle_envs):
             lin = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, t, out_format=R.OUT_RGBA32F)
             assert np.array_equal(lin[..., 3] > 0.5, ref["hit"].astype(bool))
     # a crop of the headline frame
-    rect = (7424, 4096, 7680, 4224)
+    rect = (7744, 3400, 8000, 3528)                    # inside tile 28 = (tx 4, ty 3): x in [7680, 9600), y in [3240, 4320)
     ref = REF.render(2, 15360, 8640, 0.0, envs=oracle_envs, rect=rect)
     got = sr.drawShaderTile(R.FragmentShader.FSMBPower8Shader, 28, 15360, 8640, 0.0, layout=R.LAYOUT_PACKED_TILES).reshape(1080, 1920)
     x0, y0 = rect[0] - 4 * 1920, rect[1] - 3 * 1080
