@@ -301,31 +301,36 @@ def run_ours(args):
     sr.setStream(stream.cuda_stream)
 
     sharded = world > 1
+    scene = R.FragmentShader.FSMBPower8Shader
+    full = dict(resolve_log2=SPP_LOG2, mode=mode)
     grid, skew = par.balanced_grid(FB_W, FB_H, SPP_LOG2, world) if sharded else ((0, 0), 0)
-    p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
-                      shard_rank=rank if sharded else 0, shard_count=world if sharded else 1,
-                      layout=R.LAYOUT_PACKED_TILES if sharded else R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew)
-    # N > 1: by default the gather is fused into the kernel — every rank stores its resolved tiles
-    # straight into rank 0's frame buffer over NVLink (parallel.SharedFrame); --gather nccl keeps
-    # the packed-tiles + dist.gather + re-assembly path
+    # N > 1, three ways to assemble the frame on rank 0 (--gather):
+    #   peer (default)  ONE frame-wide work queue in rank 0's memory that all GPUs claim from with system-scope atomics over
+    #                   NVLink (dynamic deal), pixel stores straight into rank 0's frame buffer, arrival flags instead of a
+    #                   barrier (parallel.SharedFrame.begin/end, csrc/frame_sync.cuh)
+    #   peer-static     round 1's path: tiles dealt statically, stores into rank 0's frame buffer, one NCCL barrier
+    #   nccl            packed tiles + ONE dist.gather + re-assembly on rank 0
+    gather = args.gather if sharded else "none"
     shared = None
-    if sharded and args.gather == "peer":
+    if gather in ("peer", "peer-static"):
+        okf = 1
         try:
             shared = par.SharedFrame(sr, OUT_W * OUT_H, world, rank)
-            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
-                              shard_rank=rank, shard_count=world, layout=R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew)
         except R.RmdfError as e:                                   # no peer access on this box
-            if rank == 0:
-                print("bench.py: peer frame buffer unavailable (%s); using the NCCL gather" % e, file=sys.stderr)
-            shared = None
-    ok = torch.tensor([1 if (shared is not None or not sharded or args.gather != "peer") else 0], device=dev)
-    if sharded:
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if args.gather == "peer" and int(ok.item()) == 0 and shared is not None:
-            shared.close(); shared = None
-        if shared is None:
-            p = sr.makeParams(R.FragmentShader.FSMBPower8Shader, None, FB_W, FB_H, TIME, resolve_log2=SPP_LOG2, mode=mode,
-                              shard_rank=rank, shard_count=world, layout=R.LAYOUT_PACKED_TILES, shard_grid=grid, shard_skew=skew)
+            okf = 0
+            print("bench.py: rank %d: peer frame buffer unavailable (%s)" % (rank, e), file=sys.stderr)
+        okt = torch.tensor([okf], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:
+            if shared is not None:
+                shared.close()
+            shared, gather = None, "nccl"
+    if gather == "peer" or not sharded:
+        p = sr.makeParams(scene, None, FB_W, FB_H, TIME, **full)                          # the same full-frame work list on every rank
+    elif gather == "peer-static":
+        p = sr.makeParams(scene, None, FB_W, FB_H, TIME, shard_rank=rank, shard_count=world, layout=R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew, **full)
+    else:
+        p = sr.makeParams(scene, None, FB_W, FB_H, TIME, shard_rank=rank, shard_count=world, layout=R.LAYOUT_PACKED_TILES, shard_grid=grid, shard_skew=skew, **full)
     # end to end at N > 1: the shared frame in page-locked HOST memory, written by every rank's kernel directly
     host_shared = None
     if shared is not None:
@@ -341,7 +346,7 @@ def run_ours(args):
     n_out, n_tiles = sr.outputPixels(p)
     out_dev = torch.empty(n_out if shared is None else 1, dtype=torch.int32, device=dev)
     shared_frame = shared.as_tensor() if (shared is not None and rank == 0) else None
-    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (sharded and rank == 0 and shared is None) else None
+    gather_list = [torch.empty(n_out, dtype=torch.int32, device=dev) for _ in range(world)] if (gather == "nccl" and rank == 0) else None
     frame_host = torch.empty(OUT_H * OUT_W, dtype=torch.int32).pin_memory() if rank == 0 else None
     cubes_pinned = [torch.from_numpy(c).pin_memory() for c in cubes]
     h2d_bytes = sum(c.numel() * 4 for c in cubes_pinned) + 64          # cube maps + rmdf_params
@@ -352,10 +357,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def render_shared(target_ptr):
+        if gather == "peer":
+            shared.begin()                                              # rank 0: queue reset + go; others: wait for go (on the stream)
+            sr.renderDevice(p, target_ptr)                              # claims from the shared queue, signals its arrival flag
+            shared.end()                                                # rank 0's stream waits for every rank's flag
+        else:
+            sr.renderDevice(p, target_ptr)
+            shared.complete()                                           # stream sync + one NCCL barrier
+
     def step_resident():
         if shared is not None:
-            sr.renderDevice(p, shared.ptr)                              # tile stores land on rank 0
-            shared.complete()                                           # one barrier, no data-path collective
+            render_shared(shared.ptr)
             return shared_frame
         sr.renderDevice(p, out_dev.data_ptr())
         if sharded:
@@ -363,20 +376,20 @@ def run_ours(args):
         return out_dev
 
     def step_e2e():
-        for s, c in enumerate(cubes_pinned):                            # H2D: this step's inputs
-            R._capi.check(sr._lib.rmdf_envmap_bind_cube(sr.handle, s, c.data_ptr(), c.shape[1]))
+        sr.bindCubeMaps(range(5), cubes_pinned)                         # H2D: this step's inputs (one batch, one sync)
         if not sharded:
             sr.renderHost(p, frame_host.data_ptr())                     # kernel + D2H through the C ABI
         elif host_shared is not None:
-            sr.renderDevice(p, host_shared.ptr)                         # every rank stores its tiles into the host frame
-            host_shared.complete()                                      # sync + one barrier: the frame is in host memory
+            render_shared(host_shared.ptr)                              # every rank stores its pixels into the host frame
+            torch.cuda.synchronize()                                    # rank 0: all arrival flags seen = the frame is in host memory
         else:
             frame = step_resident()
             if rank == 0:
                 frame_host.copy_(frame.reshape(-1), non_blocking=True)
             torch.cuda.synchronize()
 
-    def timed(fn, k, w):
+    def timed(fn, k, w, events=None):
+        events = (fn is step_resident) if events is None else events
         for _ in range(w):
             flush.zero_(); fn()
         ms = []
@@ -388,7 +401,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             e0.record(stream); fn(); e1.record(stream)
             barrier()
-            ms.append(max(e0.elapsed_time(e1), 0.0) if fn is step_resident else (time.perf_counter() - t0) * 1e3)
+            ms.append(max(e0.elapsed_time(e1), 0.0) if events else (time.perf_counter() - t0) * 1e3)
         t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -402,11 +415,41 @@ def run_ours(args):
     launches = (c["launches"] - l0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, 2)
-    e2e_same = None
+    e2e_same = frame_same = None
     if host_shared is not None:                       # the host frame the e2e path produced == the device-resident frame
         step_resident(); step_e2e(); barrier()
         if rank == 0:
             e2e_same = bool(np.array_equal(host_shared.as_numpy().view(np.int32), shared_frame.cpu().numpy()))
+    if sharded:                                       # the assembled frame == the same frame rendered by rank 0 alone
+        frame = step_resident(); barrier()
+        if rank == 0:
+            single = torch.empty(OUT_W * OUT_H, dtype=torch.int32, device=dev)
+            sr.renderDevice(sr.makeParams(scene, None, FB_W, FB_H, TIME, **full), single.data_ptr()); torch.cuda.synchronize()
+            frame_same = bool(torch.equal(frame.reshape(-1), single))
+            del single
+        barrier()
+
+    # BASELINE configs[4] at N > 1: the Julia frame through the same shared queue / peer stores / arrival flags
+    julia_n = None
+    if sharded and shared is not None and gather == "peer" and not args.no_configs:
+        shared_j = par.SharedFrame(sr, J_OUT_W * J_OUT_H, world, rank)
+
+        def step_julia():
+            shared_j.begin()
+            sr.juliaDevice(J_FB_W, J_FB_H, False, J_TICK, (0, J_FB_H), J_SPP_LOG2, shared_j.ptr)
+            shared_j.end()
+        ms_j = timed(step_julia, args.steps, 3, events=True)
+        step_julia(); barrier()
+        same_j = None
+        if rank == 0:
+            single = torch.empty(J_OUT_W * J_OUT_H, dtype=torch.int32, device=dev)
+            sr.juliaDevice(J_FB_W, J_FB_H, False, J_TICK, (0, J_FB_H), J_SPP_LOG2, single.data_ptr()); torch.cuda.synchronize()
+            same_j = bool(torch.equal(shared_j.as_tensor(), single))
+            del single
+        barrier()
+        shared_j.close()
+        julia_n = {"workload": J_WORKLOAD, "ms_per_step": ms_j, "value": J_FB_W * J_FB_H / (ms_j * 1e-3), "unit": "samples/s",
+                   "frame_equals_single_gpu": same_j, "steps": args.steps}
 
     # per-launch kernel time and counters for the roofline (rank-local kernel, all ranks reduced)
     per = args.steps + args.warmup
@@ -414,10 +457,10 @@ def run_ours(args):
                        dtype=torch.float64, device=dev)
     kms = []
     for _ in range(3):
-        flush.zero_(); sr.renderDevice(p, shared.ptr if shared is not None else out_dev.data_ptr()); torch.cuda.synchronize()
-        kms.append(sr.counters()["last_kernel_ms"])
-    if sharded:
-        dist.barrier()
+        flush.zero_(); barrier()
+        step_resident(); torch.cuda.synchronize()
+        kms.append(sr.counters()["last_kernel_ms"])       # this rank's march kernel alone (events around the launch)
+    barrier()
     kt = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -451,12 +494,15 @@ def run_ours(args):
             "metric": "mandelbulb_4k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": headline_config(mode_name, ("tiles %dx%d, rank = (tx + %d*ty) mod %d, %s" % (grid[0], grid[1], skew, world, "tile stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if sharded else "single GPU",
+            "config": headline_config(mode_name, {"none": "single GPU",
+                                                  "peer": "one frame-wide work queue in rank 0's memory, claimed by all %d GPUs with system-scope atomics over NVLink (dynamic deal); pixel stores into rank 0's frame buffer; arrival flags, no barrier" % world,
+                                                  "peer-static": "tiles %dx%d, rank = (tx + %d*ty) mod %d, stores into rank 0's frame buffer over NVLink + one NCCL barrier" % (grid[0], grid[1], skew, world),
+                                                  "nccl": "tiles %dx%d, rank = (tx + %d*ty) mod %d, one NCCL gather + re-assembly" % (grid[0], grid[1], skew, world)}[gather],
                                       "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"),
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": OUT_W * OUT_H * 4,
                     "path": ("rmdf_render with a page-locked host frame buffer: the kernel's stores are the D2H" if not sharded else
-                             ("every rank's kernel stores its tiles into one page-locked host frame (POSIX shm) over its own PCIe link + barrier; frame equals the device-resident one: %s" % e2e_same) if host_shared is not None
+                             ("every rank's kernel stores its pixels into one page-locked host frame (POSIX shm) over its own PCIe link; frame equals the device-resident one: %s" % e2e_same) if host_shared is not None
                              else "device-resident gather + D2H copy on rank 0")},
             "gpu_launches": int(launches),
             "sdf_steps_per_s": (frame_cnt["march_de"] + frame_cnt["shade_de"]) / (ms_res * 1e-3),
@@ -469,6 +515,10 @@ def run_ours(args):
                                  "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src}},
             "clocks": clocks,
         }
+        if sharded:
+            line["frame_equals_single_gpu"] = frame_same
+            if julia_n is not None:
+                line["julia_8k_64spp"] = julia_n
         if tol is not None:
             line["tolerance_check"] = tol
         if other is not None:
@@ -553,7 +603,7 @@ def run_julia(args):
     band_h = par.julia_band_height(J_FB_H, J_SPP_LOG2, world)
     n_out = J_OUT_W * J_OUT_H // world
     shared = None
-    if world > 1 and args.gather == "peer":                     # fused gather, as for the Mandelbulb frame
+    if world > 1 and args.gather in ("peer", "peer-static"):     # fused gather, as for the Mandelbulb frame
         okf = 1
         try:
             shared = par.SharedFrame(sr, J_OUT_W * J_OUT_H, world, rank)
@@ -574,7 +624,12 @@ def run_julia(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        if shared is not None:
+        if shared is not None and args.gather == "peer":                # one frame-wide queue for all GPUs (parallel.SharedFrame)
+            shared.begin()
+            sr.juliaDevice(J_FB_W, J_FB_H, False, J_TICK, (0, J_FB_H), J_SPP_LOG2, shared.ptr)
+            shared.end()
+            return shared_frame
+        if shared is not None:                                          # static interleaved bands + barrier
             sr.juliaBandsDevice(J_FB_W, J_FB_H, False, J_TICK, J_SPP_LOG2, band_h, rank, world, shared.ptr, layout=R.LAYOUT_FRAME)
             shared.complete()
             return shared_frame
@@ -623,7 +678,8 @@ def run_julia(args):
         line = {"metric": "julia_8k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": J_WORKLOAD, "fb": [J_FB_W, J_FB_H], "out": [J_OUT_W, J_OUT_H], "spp": 64,
-                                                "parallelism": ("row bands of %d rows, band b -> rank b mod %d, %s" % (band_h, world, "stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if world > 1 else "single GPU",
+                                                "parallelism": ("one frame-wide work queue in rank 0's memory claimed by all %d GPUs over NVLink, stores into rank 0's frame, arrival flags" % world if (shared is not None and args.gather == "peer") else
+                                                                "row bands of %d rows, band b -> rank b mod %d, %s" % (band_h, world, "stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if world > 1 else "single GPU",
                                                 "l2": "flushed between steps (256 MiB write)"},
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 64,
                         "d2h_bytes_per_step": J_OUT_W * J_OUT_H * 4},
@@ -653,7 +709,8 @@ def main():
                     help="auto: the fast build if it meets BASELINE's tolerance against the parity build in this run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs (N = 1 only)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: fused peer-memory stores (default) or NCCL gather")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-static", "nccl"],
+                    help="N > 1: shared work queue + stores over NVLink peer memory (default), round 1's static deal + barrier, or NCCL gather")
     ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
                     help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")
     args = ap.parse_args()

@@ -113,6 +113,8 @@ int  rmdf_envmap_bind(rmdf_ctx *ctx, int slot, const float *latlong_rgb, int w, 
 /* Bind ready-made faces (6·face_w·face_w·3 floats, order +X,-X,+Y,-Y,+Z,-Z, row 0 =
  * t 0); values are rounded to half like GL's RGB16F upload. */
 int  rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w);
+/* The same for n slots in one batch with ONE synchronisation at the end (per-frame uploads of all five maps). */
+int  rmdf_envmap_bind_cubes(rmdf_ctx *ctx, int n, const int *slots, const float *const *faces_rgb, const int *face_w);
 /* Read a bound cube map back (the half values widened to float). faces_rgb may be
  * NULL to query face_w only. */
 int  rmdf_envmap_get_cube(rmdf_ctx *ctx, int slot, float *faces_rgb, int *face_w);
@@ -224,6 +226,28 @@ typedef struct {
 /* Totals since the last rmdf_counters_reset (synchronises the stream). */
 int  rmdf_counters_get(rmdf_ctx *ctx, rmdf_counters *out);
 int  rmdf_counters_reset(rmdf_ctx *ctx);
+
+/* ---- one frame rendered by several GPUs, assembled over NVLink peer memory (no reference counterpart) ----------
+ * A control block of RMDF_SYNC_WORDS uint32 words (zero-initialised) lives in memory that every participating GPU can
+ * reach — allocate it on rank 0 with rmdf_shared_alloc next to the frame buffer, map it elsewhere with
+ * rmdf_shared_open.  Word 0 = work queue, word 1 = "go", words 8+r = arrival flag of rank r.  Per frame, with a
+ * sequence number seq that grows by one (start at 1):
+ *   every rank   rmdf_frame_begin(ctx, ctrl, rank, world, seq, timeout_ms)   rank 0's stream zeroes the queue and publishes
+ *                                                            seq; the other ranks' streams wait for it.  Arms the next
+ *                                                            rmdf_render_device / rmdf_julia_device of this context:
+ *   every rank   rmdf_render_device(ctx, params, frame)      the SAME full-frame params on every rank (RMDF_LAYOUT_FRAME,
+ *                                                            shard_count 1), `frame` = the shared buffer.  All GPUs claim
+ *                                                            work items from the one queue with system-scope atomics (a
+ *                                                            dynamic deal), store into the shared frame, and the last CTA
+ *                                                            of each kernel publishes seq in the rank's arrival flag.
+ *   rank 0       rmdf_frame_end(ctx, ctrl, world, seq, timeout_ms)   its stream waits for all arrival flags: work queued
+ *                                                            behind it sees the complete frame.  No host round trip.
+ * Waits give up after timeout_ms (default 10 s when <= 0); rmdf_frame_sync_status synchronises the stream and returns
+ * 0, or 1 + the index of the word a wait gave up on. */
+#define RMDF_SYNC_WORDS 64
+int  rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int timeout_ms);
+int  rmdf_frame_end(rmdf_ctx *ctx, void *ctrl_dev, int world, uint32_t seq, int timeout_ms);
+int  rmdf_frame_sync_status(rmdf_ctx *ctx, int *timed_out_word);
 
 /* FP32 FMA roofline denominator: an FFMA-chain microbenchmark on ctx's device (the
  * reference has no counterpart).  tflops = 2·FFMA/s, sm_mhz = SM clock sustained. */

@@ -22,11 +22,12 @@ FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST = 1, 2, 4
 EXPORTS = [
     "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
     "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device", "rmdf_envmap_convolve_rows_device",
-    "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
+    "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_bind_cubes", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
     "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak", "rmdf_measure_mufu_peak",
     "rmdf_shared_alloc", "rmdf_shared_free", "rmdf_shared_open", "rmdf_shared_close", "rmdf_enable_peer",
     "rmdf_host_register", "rmdf_host_unregister",
+    "rmdf_frame_begin", "rmdf_frame_end", "rmdf_frame_sync_status",
 ]
 
 
@@ -86,6 +87,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_rgbe_roundtrip.argtypes = [vp, C.c_int64]
     L.rmdf_envmap_bind.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
     L.rmdf_envmap_bind_cube.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.rmdf_envmap_bind_cubes.argtypes = [vp, C.c_int, ip, C.POINTER(vp), ip]
     L.rmdf_envmap_get_cube.argtypes = [vp, C.c_int, vp, ip]
     L.rmdf_envmap_unbind.argtypes = [vp, C.c_int]
     L.rmdf_set_cornell.argtypes = [vp, vp, C.c_int]
@@ -108,6 +110,9 @@ def load(build_if_missing: bool = True):
     L.rmdf_enable_peer.argtypes = [vp, C.c_int]
     L.rmdf_host_register.argtypes = [vp, vp, C.c_int64, C.POINTER(vp)]
     L.rmdf_host_unregister.argtypes = [vp, vp]
+    L.rmdf_frame_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int]
+    L.rmdf_frame_end.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_int]
+    L.rmdf_frame_sync_status.argtypes = [vp, ip]
     for name in EXPORTS:
         f = getattr(L, name)
         if name not in ("rmdf_destroy", "rmdf_last_error", "rmdf_render_output_pixels"):

@@ -28,6 +28,7 @@ UNITS = {
     "march_fast.cu": ["--use_fast_math"],
     "envmap.cu": ["-fmad=false"],
     "julia.cu": ["-fmad=false"],
+    "frame_sync.cu": [],
     "peak.cu": [],
 }
 

@@ -110,11 +110,12 @@ julia_kernel(const JuliaParams P)
     const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
+    unsigned claimed = 0;
+    if (lane == 0) claimed = claim_item(P.sync);
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(P.queue, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        const unsigned item = __shfl_sync(0xffffffffu, claimed, 0);
         if (item >= (unsigned)P.n_items) break;
+        if (lane == 0) claimed = claim_item(P.sync);             // the next item: its latency overlaps this one
         // item → (band of this rank, block row inside the band, block column)
         const int per_band = P.blocks_x * P.blocks_y;
         const int band_k = (int)item / per_band, in_band = (int)item - band_k * per_band;
@@ -218,6 +219,7 @@ julia_kernel(const JuliaParams P)
         atomicAdd(P.counters + C_SAMPLES, (unsigned long long)samples);
         atomicAdd(P.counters + C_ITERS, (unsigned long long)iters);
     }
+    signal_when_grid_done(P.sync);
 }
 #undef RMDF_JULIA_BLOCK
 #undef RMDF_JULIA_STEP

@@ -49,7 +49,11 @@ struct rmdf_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
-    unsigned int *d_queue = nullptr;
+    unsigned int *d_queue = nullptr;   // [0] work queue, [1] CTA-exit counter of the running kernel, [2] wait status
+    // multi-GPU frame assembly (rmdf_frame_begin): applies to the next render / Julia launch, then clears
+    unsigned int *sync_ctrl = nullptr;
+    int sync_rank = 0, sync_world = 1;
+    unsigned int sync_seq = 0;
     unsigned long long *d_counters = nullptr;
     uint64_t launches = 0;
     EnvSlot env[RMDF_ENV_SLOTS];
@@ -113,7 +117,8 @@ extern "C" int rmdf_create(rmdf_ctx **out, int device)
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev0);
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev1);
-    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_queue, sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_queue, 4 * sizeof(unsigned int));
+    if (err == cudaSuccess) err = cudaMemset(ctx->d_queue, 0, 4 * sizeof(unsigned int));
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * C_NSLOTS);
     if (err == cudaSuccess) err = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS);
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_cornell, sizeof(float4) * kCornellF4);
@@ -320,12 +325,11 @@ static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *fa
     return RMDF_OK;
 }
 
-extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w)
+// enqueue the upload of one slot on the stream (no synchronisation at the end)
+static int bind_cube_async(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w)
 {
-    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= RMDF_ENV_SLOTS) return fail(RMDF_ERR_ARG, "env slot %d out of range", slot);
     if (!faces_rgb || face_w < 1 || face_w > 8192) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind_cube: bad faces (w = %d)", face_w);
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     EnvSlot &s = ctx->env[slot];
     const size_t bytes = sizeof(float) * 3 * 6 * (size_t)face_w * face_w;
     if (s.face_w != face_w) {                       // first bind or a size change: reallocate
@@ -336,9 +340,24 @@ extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces
     // stream-ordered: a render already queued on the stream keeps sampling the old texels
     cudaError_t e = cudaMemcpyAsync(s.faces_dev, faces_rgb, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { free_slot(s); return fail(RMDF_ERR_CUDA, "rmdf_envmap_bind_cube: %s", cudaGetErrorString(e)); }
-    rc = make_slot_textures(ctx, s, face_w, s.faces_dev);
-    if (rc) return rc;
+    return make_slot_textures(ctx, s, face_w, s.faces_dev);
+}
+extern "C" int rmdf_envmap_bind_cube(rmdf_ctx *ctx, int slot, const float *faces_rgb, int face_w)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if ((rc = bind_cube_async(ctx, slot, faces_rgb, face_w))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));         // the caller's buffer is not referenced after return
+    return RMDF_OK;
+}
+extern "C" int rmdf_envmap_bind_cubes(rmdf_ctx *ctx, int n, const int *slots, const float *const *faces_rgb, const int *face_w)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (n < 1 || n > RMDF_ENV_SLOTS || !slots || !faces_rgb || !face_w) return fail(RMDF_ERR_ARG, "rmdf_envmap_bind_cubes: bad arguments");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    for (int i = 0; i < n; i++)
+        if ((rc = bind_cube_async(ctx, slots[i], faces_rgb[i], face_w[i]))) { cudaStreamSynchronize(ctx->stream); return rc; }
+    CU(cudaStreamSynchronize(ctx->stream));         // one synchronisation for the batch; the buffers are free again
     return RMDF_OK;
 }
 
@@ -479,7 +498,18 @@ struct WorkList {
     int n_tiles, tile_w, tile_h;
     int64_t out_pixels;
     int out_stride;
+    // rect_mode 1: the pixels that are STORED, [clip_x0,clip_x1)×[clip_y0,clip_y1).  The rendered rect
+    // (tile_x0.., tile_w×tile_h) is this rectangle grown to even pixel boundaries: a 2×2 fragment quad that
+    // straddles a tile edge is shaded whole (GL's helper invocations) so that its min/mag decision — and with it
+    // every pixel — is the same as in the full-frame draw.
+    int clip_x0, clip_y0, clip_x1, clip_y1;
+    int64_t out_base;                 // index of the rendered rect's origin in the output (may be negative by the growth)
 };
+
+// First pixel whose centre lies at or beyond edge t of the reference's 8-tile split of `dim` pixels
+// (ShaderRendering.hs:183-195: NDC edge −1 + t/8·2 → window coordinate t·dim/8; a pixel belongs to the tile
+// that contains its centre, a centre exactly on an edge goes to the tile on its upper side): ceil(t·dim/8 − ½).
+static int tile_edge(int t, int dim) { return (int)((2LL * t * dim + 7) >> 4); }
 
 static int build_worklist(const rmdf_params *p, WorkList *wl)
 {
@@ -513,26 +543,51 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
             if ((p->row_begin % (2 * q)) || (p->row_end % (2 * q))) return fail(RMDF_ERR_ARG, "row range must be a multiple of %d rows", 2 * q);
             wl->rect_mode = 1; wl->n_tiles = 1;
             wl->tile_x0 = 0; wl->tile_y0 = p->row_begin; wl->tile_w = p->fb_w; wl->tile_h = p->row_end - p->row_begin;
+            wl->clip_x0 = 0; wl->clip_x1 = p->fb_w; wl->clip_y0 = p->row_begin; wl->clip_y1 = p->row_end;
+            wl->out_base = (int64_t)(wl->tile_y0 >> k) * wl->out_stride;
             return RMDF_OK;
         }
         wl->rect_mode = 0; wl->n_tiles = 1; wl->tile_w = p->fb_w; wl->tile_h = p->fb_h;
         return RMDF_OK;
     }
-    // Tile edges must fall on even pixel boundaries so that no 2×2 fragment quad straddles two tiles.
-    int gx = 8, gy = 8;                                   // ShaderRendering.hs:49-52
-    if (sharded) {
-        gx = p->shard_grid_x ? p->shard_grid_x : 8;
-        gy = p->shard_grid_y ? p->shard_grid_y : 8;
-        wl->shard_skew = p->shard_grid_x ? p->shard_skew : 1;
-        if (gx < 1 || gy < 1 || gx > 1024 || gy > 1024) return fail(RMDF_ERR_ARG, "shard grid %dx%d out of range", gx, gy);
-        if (gx % p->shard_count) return fail(RMDF_ERR_ARG, "shard_grid_x %d is not a multiple of shard_count %d", gx, p->shard_count);
-        if (wl->shard_skew < 0) return fail(RMDF_ERR_ARG, "shard_skew must be >= 0");
+    if (!sharded) {
+        // one tile of the reference's 8×8 grid (idx `mod` nTiles, :186-188), any frame size
+        const int t = p->tile_idx % 64, tx = t & 7, ty = t >> 3;
+        wl->clip_x0 = tile_edge(tx, p->fb_w); wl->clip_x1 = tile_edge(tx + 1, p->fb_w);
+        wl->clip_y0 = tile_edge(ty, p->fb_h); wl->clip_y1 = tile_edge(ty + 1, p->fb_h);
+        const int cw = wl->clip_x1 - wl->clip_x0, ch = wl->clip_y1 - wl->clip_y0;
+        if ((wl->clip_x0 % q) || (wl->clip_y0 % q) || (cw % q) || (ch % q))
+            return fail(RMDF_ERR_ARG, "tile [%d,%d)x[%d,%d) is not a multiple of the %dx%d resolve footprint", wl->clip_x0, wl->clip_x1, wl->clip_y0, wl->clip_y1, q, q);
+        wl->rect_mode = 1; wl->n_tiles = 1;
+        wl->tile_x0 = wl->clip_x0 & ~1; wl->tile_y0 = wl->clip_y0 & ~1;
+        const int ex1 = (wl->clip_x1 + 1) & ~1, ey1 = (wl->clip_y1 + 1) & ~1;
+        wl->tile_w = (ex1 < p->fb_w ? ex1 : p->fb_w) - wl->tile_x0;
+        wl->tile_h = (ey1 < p->fb_h ? ey1 : p->fb_h) - wl->tile_y0;
+        if (cw <= 0 || ch <= 0) { wl->tile_w = wl->tile_h = 0; }
+        if (p->layout == RMDF_LAYOUT_PACKED_TILES) {
+            wl->out_stride = cw >> k;
+            wl->out_pixels = (int64_t)(cw >> k) * (ch >> k);
+            wl->out_base = -((int64_t)((wl->clip_y0 - wl->tile_y0) >> k) * wl->out_stride + ((wl->clip_x0 - wl->tile_x0) >> k));
+        } else {
+            wl->out_stride = p->fb_w >> k;
+            wl->out_pixels = (int64_t)(p->fb_w >> k) * (p->fb_h >> k);
+            wl->out_base = (int64_t)(wl->tile_y0 >> k) * wl->out_stride + (wl->tile_x0 >> k);
+        }
+        return RMDF_OK;
     }
+    // Shard grids (multi-GPU; not a reference concept): tile edges must fall on even pixel boundaries so that no
+    // 2×2 fragment quad straddles two tiles.
+    int gx = p->shard_grid_x ? p->shard_grid_x : 8;
+    int gy = p->shard_grid_y ? p->shard_grid_y : 8;
+    wl->shard_skew = p->shard_grid_x ? p->shard_skew : 1;
+    if (gx < 1 || gy < 1 || gx > 1024 || gy > 1024) return fail(RMDF_ERR_ARG, "shard grid %dx%d out of range", gx, gy);
+    if (gx % p->shard_count) return fail(RMDF_ERR_ARG, "shard_grid_x %d is not a multiple of shard_count %d", gx, p->shard_count);
+    if (wl->shard_skew < 0) return fail(RMDF_ERR_ARG, "shard_skew must be >= 0");
     if ((p->fb_w % (2 * gx)) || (p->fb_h % (2 * gy)))
-        return fail(RMDF_ERR_UNSUPPORTED, "tiled rendering needs frame dimensions divisible by %dx%d (got %dx%d)", 2 * gx, 2 * gy, p->fb_w, p->fb_h);
+        return fail(RMDF_ERR_UNSUPPORTED, "sharded rendering needs frame dimensions divisible by %dx%d (got %dx%d)", 2 * gx, 2 * gy, p->fb_w, p->fb_h);
     wl->tile_w = p->fb_w / gx; wl->tile_h = p->fb_h / gy;
     if ((wl->tile_w % q) || (wl->tile_h % q)) return fail(RMDF_ERR_ARG, "tile %dx%d is not a multiple of the %dx%d resolve footprint", wl->tile_w, wl->tile_h, q, q);
-    if (sharded) {
+    {
         int ty0 = 0, ty1 = gy;
         if (striped) {
             if ((p->row_begin % wl->tile_h) || (p->row_end % wl->tile_h)) return fail(RMDF_ERR_ARG, "row range must be a multiple of the shard tile height %d", wl->tile_h);
@@ -540,10 +595,6 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
         }
         wl->rect_mode = 2; wl->shard_gx = gx; wl->shard_ty0 = ty0;
         wl->n_tiles = (ty1 - ty0) * (gx / p->shard_count);
-    } else {
-        const int t = p->tile_idx % 64;                   // idx `mod` nTiles, :186-188
-        wl->rect_mode = 1; wl->n_tiles = 1;
-        wl->tile_x0 = (t & 7) * wl->tile_w; wl->tile_y0 = (t >> 3) * wl->tile_h;
     }
     if (p->layout == RMDF_LAYOUT_PACKED_TILES) {
         wl->out_stride = wl->tile_w >> k;
@@ -622,6 +673,10 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.lod_policy = p->lod_policy; mp.resolve_log2 = p->resolve_log2;
     mp.out_format = p->out_format; mp.layout = p->layout; mp.flags = p->flags;
     mp.rect_mode = wl.rect_mode; mp.tile_x0 = wl.tile_x0; mp.tile_y0 = wl.tile_y0;
+    mp.clip_x0 = wl.clip_x0; mp.clip_y0 = wl.clip_y0; mp.clip_x1 = wl.clip_x1; mp.clip_y1 = wl.clip_y1;
+    mp.rect_out_base = wl.out_base;
+    mp.clipped = (wl.rect_mode == 1) && (wl.clip_x0 != wl.tile_x0 || wl.clip_y0 != wl.tile_y0 ||
+                                         wl.clip_x1 != wl.tile_x0 + wl.tile_w || wl.clip_y1 != wl.tile_y0 + wl.tile_h);
     mp.shard_gx = wl.shard_gx; mp.shard_count = p->shard_count; mp.shard_rank = p->shard_rank; mp.shard_skew = wl.shard_skew;
     mp.shard_ty0 = wl.shard_ty0;
     mp.tile_w = wl.tile_w; mp.tile_h = wl.tile_h;
@@ -633,24 +688,46 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     }
     mp.cornell = ctx->d_cornell;
     mp.out = fb_dev;
-    mp.queue = ctx->d_queue;
+    mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
+    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0;
+    int world = 1;
+    if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
+        if (wl.rect_mode != 0 || p->layout != RMDF_LAYOUT_FRAME)
+            return fail(RMDF_ERR_ARG, "a multi-GPU frame (rmdf_frame_begin) needs the full frame in RMDF_LAYOUT_FRAME (no tile, shard or row range)");
+        mp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; mp.sync.queue_sys = 1;
+        mp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; mp.sync.signal_value = ctx->sync_seq;
+        world = ctx->sync_world;
+        ctx->sync_ctrl = nullptr;
+    }
     mp.counters = ctx->d_counters;
 
     const int ctas_per_sm = (p->mode == RMDF_MODE_FAST) ? march_fast_ctas_per_sm(p->scene, p->flags) : march_parity_ctas_per_sm(p->scene, p->flags);
-    const int resident_warps = ctas_per_sm * ctx->sm_count * kWarpsPerCta;
-    int bx = (wl.tile_w + kBlockDim - 1) / kBlockDim;
-    const int64_t blocks32 = (int64_t)bx * ((wl.tile_h + 31) / 32) * wl.n_tiles;
-    mp.item_h = pick_item_h(blocks32, resident_warps, p->resolve_log2);
-    // A frame too small to give every resident warp a few items even at the smallest item height (BASELINE config 1:
-    // 512×512 = 2048 items of 32×4 samples for 4736 warps) gets narrower items too: 16 or 8 columns (one 8×4 tile row).
-    mp.item_w = kBlockDim;
+    const int resident_warps = ctas_per_sm * ctx->sm_count * kWarpsPerCta * world;     // all GPUs that draw from the queue
+    // Work-item size.  Measured on BASELINE config 4 (profiles/r2_item_size.md): 32×32-sample items 17.34 ms, 32×16
+    // 16.86, 32×8 16.70, 32×4 16.74, 16×4 17.11 — small items interleave the per-item resolve/store bursts of the
+    // warps and keep the end of the frame short, very small ones pay the claim/decode/store overhead more often.  So
+    // items start at 32×8 and shrink (rows to 4, then columns to 16 and 8: one 8×4 tile row) while there are fewer
+    // than 24 items per resident warp: mid-size frames (config 3, 3840×2160) land on 16×4, config 1 (512²) on 8×4.
+    int bx;
     {
-        const int min_h = (1 << p->resolve_log2) > 4 ? (1 << p->resolve_log2) : 4;
-        const int min_w = (1 << p->resolve_log2) > 8 ? (1 << p->resolve_log2) : 8;
-        while (mp.item_h == min_h && mp.item_w > min_w &&
-               (int64_t)((wl.tile_w + mp.item_w - 1) / mp.item_w) * ((wl.tile_h + mp.item_h - 1) / mp.item_h) * wl.n_tiles < (int64_t)resident_warps * 4)
-            mp.item_w >>= 1;
+        const int q = 1 << p->resolve_log2;
+        const int min_h = q > 4 ? q : 4, min_w = q > 8 ? q : 8;
+        mp.item_h = 8 > min_h ? 8 : min_h; mp.item_w = kBlockDim;
+        auto items = [&]() { return (int64_t)((wl.tile_w + mp.item_w - 1) / mp.item_w) * ((wl.tile_h + mp.item_h - 1) / mp.item_h) * wl.n_tiles; };
+        while (items() < (int64_t)resident_warps * 24) {
+            if (mp.item_h > min_h) mp.item_h >>= 1;
+            else if (mp.item_w > min_w) mp.item_w >>= 1;
+            else break;
+        }
         bx = (wl.tile_w + mp.item_w - 1) / mp.item_w;
+    }
+    if (const char *e = getenv("RMDF_ITEM_H")) {          // tuning overrides (experiments only)
+        const int v = atoi(e), min_h = (1 << p->resolve_log2) > 4 ? (1 << p->resolve_log2) : 4;
+        if (v >= min_h && v <= 32 && (v & (v - 1)) == 0) mp.item_h = v;
+    }
+    if (const char *e = getenv("RMDF_ITEM_W")) {
+        const int v = atoi(e), min_w = (1 << p->resolve_log2) > 8 ? (1 << p->resolve_log2) : 8;
+        if (v >= min_w && v <= 32 && (v & (v - 1)) == 0) { mp.item_w = v; bx = (wl.tile_w + mp.item_w - 1) / mp.item_w; }
     }
     mp.blocks_x = bx;
     mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
@@ -662,7 +739,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
 
-    CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = (p->mode == RMDF_MODE_FAST) ? launch_march_fast(mp, grid, ctx->stream)
                                                 : launch_march_parity(mp, grid, ctx->stream);
@@ -740,16 +817,21 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->xshift = 1.45f * jp->ratio;
     const int my_bands = n_bands / shard_count;
     const int ctas = julia_ctas_per_sm();
-    const int resident_warps = ctas * ctx->sm_count * kWarpsPerCta;
+    const int resident_warps = ctas * ctx->sm_count * kWarpsPerCta * (ctx->sync_ctrl ? ctx->sync_world : 1);
     const int bx = (w + kBlockDim - 1) / kBlockDim;
     jp->item_h = pick_item_h((int64_t)bx * ((band_h + 31) / 32) * my_bands, resident_warps, k);
+    if (const char *e = getenv("RMDF_JULIA_ITEM_H")) {    // tuning override (experiments only)
+        const int v = atoi(e), min_h = (1 << k) > 4 ? (1 << k) : 4;
+        if (v >= min_h && v <= 32 && (v & (v - 1)) == 0 && band_h % v == 0) jp->item_h = v;
+    }
     jp->blocks_x = bx;
     jp->blocks_y = (band_h + jp->item_h - 1) / jp->item_h;
     const int64_t n = (int64_t)jp->blocks_x * jp->blocks_y * my_bands;
     if (n > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "julia frame too large");
     jp->n_items = (int)n;
     jp->out_stride = w >> k;
-    jp->queue = ctx->d_queue;
+    jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
+    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
 }
@@ -758,10 +840,19 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
 {
     jp.out = (uint32_t *)fb_dev;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
+        if (jp.shard_count != 1 || !jp.frame_layout || jp.y0 != 0 || jp.y1 != jp.h) {
+            ctx->sync_ctrl = nullptr;
+            return fail(RMDF_ERR_ARG, "a multi-GPU Julia frame (rmdf_frame_begin) needs the whole frame, one band list, frame layout");
+        }
+        jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1;
+        jp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; jp.sync.signal_value = ctx->sync_seq;
+        ctx->sync_ctrl = nullptr;
+    }
     int grid = julia_ctas_per_sm() * ctx->sm_count;
     const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
-    CU(cudaMemsetAsync(ctx->d_queue, 0, sizeof(unsigned int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_julia(jp, grid, ctx->stream);
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "julia kernel launch: %s", cudaGetErrorString(e));
@@ -778,6 +869,7 @@ extern "C" int rmdf_julia_device(rmdf_ctx *ctx, int w, int h, int smooth, double
     if (!fb_dev) return fail(RMDF_ERR_ARG, "frame buffer pointer is NULL");
     JuliaParams jp;
     if ((rc = julia_params(ctx, w, h, smooth, tick, y0, y1, resolve_log2, 0, 0, 1, &jp))) return rc;
+    jp.frame_layout = 1;                                    // one band = the row range itself: both layouts coincide
     return julia_launch(ctx, jp, fb_dev);
 }
 
@@ -831,8 +923,10 @@ extern "C" int rmdf_shared_alloc(rmdf_ctx *ctx, int64_t bytes, void **dev_ptr, u
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     void *p = nullptr;
     CU(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);        // a control block inside starts at sequence number 0
+    if (e != cudaSuccess) { cudaFree(p); return fail(RMDF_ERR_CUDA, "rmdf_shared_alloc: %s", cudaGetErrorString(e)); }
     cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) { cudaFree(p); return fail(RMDF_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
     memcpy(handle, &h, 64);
     *dev_ptr = p;
@@ -891,6 +985,46 @@ extern "C" int rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr)
     if (!host_ptr) return fail(RMDF_ERR_ARG, "rmdf_host_unregister: NULL");
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaHostUnregister(host_ptr));
+    return RMDF_OK;
+}
+
+// ---- one frame over several GPUs: shared work queue + arrival flags in peer memory (csrc/frame_sync.cuh) --------
+extern "C" int rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int timeout_ms)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!ctrl_dev || world < 1 || world > 32 || rank < 0 || rank >= world) return fail(RMDF_ERR_ARG, "rmdf_frame_begin: bad arguments (rank %d of %d)", rank, world);
+    if (timeout_ms <= 0) timeout_ms = 10000;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    unsigned int *ctrl = (unsigned int *)ctrl_dev;
+    cudaError_t e;
+    if (rank == 0) e = launch_frame_begin(ctrl, seq, ctx->stream);                       // queue = 0, then go = seq
+    else           e = launch_wait_flags(ctrl + kSyncGoWord, 1, seq, (unsigned)timeout_ms, ctx->d_queue + 2, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_frame_begin: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    ctx->sync_ctrl = ctrl; ctx->sync_rank = rank; ctx->sync_world = world; ctx->sync_seq = seq;
+    return RMDF_OK;
+}
+extern "C" int rmdf_frame_end(rmdf_ctx *ctx, void *ctrl_dev, int world, uint32_t seq, int timeout_ms)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!ctrl_dev || world < 1 || world > 32) return fail(RMDF_ERR_ARG, "rmdf_frame_end: bad arguments");
+    if (timeout_ms <= 0) timeout_ms = 10000;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaError_t e = launch_wait_flags((unsigned int *)ctrl_dev + kSyncFlagWord0, world, seq, (unsigned)timeout_ms, ctx->d_queue + 2, ctx->stream);
+    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_frame_end: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return RMDF_OK;
+}
+extern "C" int rmdf_frame_sync_status(rmdf_ctx *ctx, int *timed_out_word)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!timed_out_word) return fail(RMDF_ERR_ARG, "rmdf_frame_sync_status: NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    unsigned int v = 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(&v, ctx->d_queue + 2, sizeof v, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(ctx->d_queue + 2, 0, sizeof v));
+    *timed_out_word = (int)v;
     return RMDF_OK;
 }
 

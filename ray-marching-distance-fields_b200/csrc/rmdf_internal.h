@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "frame_sync.cuh"
 
 namespace rmdf {
 
@@ -29,7 +30,10 @@ struct MarchParams {
     // work list: the whole frame (0), one tile of the reference's 8×8 grid (1), or this rank's
     // tiles of the shard grid (2): (tx + skew·ty) mod count == rank, packed by ascending (ty, tx)
     int   rect_mode;
-    int   tile_x0, tile_y0;           // rect_mode 1: origin of the tile
+    int   tile_x0, tile_y0;           // rect_mode 1: origin of the rendered rect (the tile grown to even pixel boundaries)
+    int   clip_x0, clip_y0, clip_x1, clip_y1;   // rect_mode 1: the pixels that are stored (the tile itself)
+    int   clipped;                    // rect_mode 1: the rendered rect is larger than the stored one (odd tile edges)
+    long long rect_out_base;          // rect_mode 1: output index of the rendered rect's origin
     int   shard_gx, shard_count, shard_rank, shard_skew, shard_ty0;   // shard_ty0: first tile row of a stripe
     int   tile_w, tile_h;             // level-0 size of one tile
     int   item_h;                     // rows per work item: 4, 8, 16 or 32
@@ -43,7 +47,7 @@ struct MarchParams {
     int   env_face[5];                // face width, 0 = unbound (samples as constant 1.0)
     const float4 *cornell;            // kCornellF4 float4 (precomputed triangle terms)
     void *out;
-    unsigned int *queue;              // work-queue counter (zeroed before the launch)
+    FrameSync sync;                   // work queue + completion signal (frame_sync.cuh)
     unsigned long long *counters;     // C_NSLOTS totals
 };
 
@@ -55,7 +59,7 @@ struct JuliaParams {
     int   item_h, blocks_x, blocks_y, n_items;
     int   out_stride;
     uint32_t *out;
-    unsigned int *queue;
+    FrameSync sync;
     unsigned long long *counters;
 };
 
@@ -73,6 +77,8 @@ cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int f
 cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s);
 cudaError_t measure_fp32_peak(int sm_count, cudaStream_t s, float *tflops, float *sm_mhz);
 cudaError_t measure_mufu_peak(int sm_count, cudaStream_t s, float *gops);
+cudaError_t launch_frame_begin(unsigned int *ctrl, unsigned int seq, cudaStream_t s);
+cudaError_t launch_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int timeout_ms, unsigned int *status, cudaStream_t s);
 cudaError_t launch_mip_resolve(const uint32_t *in_dev, int w, int h, int levels, uint32_t *out_dev, cudaStream_t s);
 
 }  // namespace rmdf

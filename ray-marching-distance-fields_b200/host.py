@@ -263,6 +263,20 @@ class ShaderRenderer:
         assert faces.ndim == 4 and faces.shape[0] == 6 and faces.shape[1] == faces.shape[2] and faces.shape[3] == 3
         check(self._lib.rmdf_envmap_bind_cube(self._h, slot, faces.ctypes.data, faces.shape[1]))
 
+    def bindCubeMaps(self, slots, faces_list) -> None:
+        """Several slots in one batch (one synchronisation): per-frame uploads from pinned host memory.
+        faces_list: numpy arrays or torch CPU tensors [6, w, w, 3] float32."""
+        n = len(faces_list)
+        ptrs = (C.c_void_p * n)(); ws = (C.c_int * n)(); sl = (C.c_int * n)(*[int(x) for x in slots])
+        keep = []
+        for i, f in enumerate(faces_list):
+            if hasattr(f, "data_ptr"):
+                ptrs[i] = f.data_ptr(); ws[i] = f.shape[1]
+            else:
+                f = _as_f32(f); keep.append(f)
+                ptrs[i] = f.ctypes.data; ws[i] = f.shape[1]
+        check(self._lib.rmdf_envmap_bind_cubes(self._h, n, sl, ptrs, ws))
+
     def unbindCubeMap(self, slot: int) -> None:
         check(self._lib.rmdf_envmap_unbind(self._h, slot))
 
@@ -391,6 +405,19 @@ class ShaderRenderer:
 
     def sharedClose(self, ptr: int) -> None:
         check(self._lib.rmdf_shared_close(self._h, C.c_void_p(ptr)))
+
+    def frameBegin(self, ctrl_ptr: int, rank: int, world: int, seq: int, timeout_ms: int = 10000) -> None:
+        """One frame over several GPUs (include/rmdf.h rmdf_frame_begin): arms this context's next render."""
+        check(self._lib.rmdf_frame_begin(self._h, C.c_void_p(ctrl_ptr), rank, world, seq, timeout_ms))
+
+    def frameEnd(self, ctrl_ptr: int, world: int, seq: int, timeout_ms: int = 10000) -> None:
+        check(self._lib.rmdf_frame_end(self._h, C.c_void_p(ctrl_ptr), world, seq, timeout_ms))
+
+    def frameSyncStatus(self) -> int:
+        """0, or 1 + the index of the control word a wait gave up on (synchronises the stream)."""
+        v = C.c_int(0)
+        check(self._lib.rmdf_frame_sync_status(self._h, C.byref(v)))
+        return int(v.value)
 
     def enablePeer(self, peer_device: int) -> None:
         check(self._lib.rmdf_enable_peer(self._h, peer_device))

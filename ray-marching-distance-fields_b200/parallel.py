@@ -129,28 +129,55 @@ def gather_bands(packed, w: int, h: int, world: int, rank: int, band_h: int, gat
     return torch.stack(gather_list).reshape(world, nb, band_h, w).permute(1, 0, 2, 3).reshape(h, w)
 
 
-# ---- fused gather: every rank's kernel stores its tiles straight into rank 0's frame buffer ----
+# ---- fused gather: every rank's kernel stores its pixels straight into rank 0's frame buffer ----
+SYNC_WORDS = 64          # include/rmdf.h RMDF_SYNC_WORDS
+
+
 class SharedFrame:
-    """The resolved frame buffer lives on rank 0's GPU; the other ranks map it through CUDA IPC and
-    pass `self.ptr` as the render target (LAYOUT_FRAME + shard_*), so the march kernel's 128-bit
-    tile stores cross NVLink while the rest of the frame is still being marched.  After the launch
-    only a barrier is needed (`complete()`): there is no separate gather or re-assembly pass."""
+    """The resolved frame buffer lives on rank 0's GPU; the other ranks map it through CUDA IPC and pass `self.ptr`
+    as the render target, so the kernels' 128-bit stores cross NVLink while the rest of the frame is still being
+    marched.  Behind the frame sits a control block (work queue, "go" word, one arrival flag per rank):
+
+      static deal   renderDevice(params with shard_rank/shard_count, self.ptr); complete()   — one barrier
+      dynamic deal  begin(); renderDevice(the SAME full-frame params on every rank, self.ptr); end()
+                    all GPUs claim work items from ONE queue with system-scope atomics over NVLink (a GPU that draws
+                    cheap items claims more), each kernel's last CTA publishes the frame number in its rank's arrival
+                    flag, and rank 0's stream waits on the flags: no NCCL call, no host round trip on the data path.
+    """
 
     def __init__(self, sr, n_words: int, world: int, rank: int):
         import torch.distributed as dist
         self.sr, self.world, self.rank, self.n_words = sr, world, rank, n_words
+        self.seq = 0
+        frame_bytes = (n_words * 4 + 255) & ~255
         box = [None]
         if rank == 0:
-            self.ptr, handle = sr.sharedAlloc(n_words * 4)
+            self.ptr, handle = sr.sharedAlloc(frame_bytes + SYNC_WORDS * 4)      # zero-initialised by the library
             box[0] = handle
         if world > 1:
             dist.broadcast_object_list(box, src=0)
             if rank != 0:
                 self.ptr = sr.sharedOpen(box[0])
+        self.ctrl = self.ptr + frame_bytes
 
+    # -- dynamic deal ---------------------------------------------------------------------------------
+    def begin(self, timeout_ms: int = 10000) -> int:
+        """Every rank, before its render call of the frame.  Returns the frame's sequence number."""
+        self.seq += 1
+        self.sr.frameBegin(self.ctrl, self.rank, self.world, self.seq, timeout_ms)
+        return self.seq
+
+    def end(self, timeout_ms: int = 10000) -> None:
+        """Rank 0: work queued on its stream after this sees the complete frame.  Other ranks: nothing to do."""
+        if self.rank == 0:
+            self.sr.frameEnd(self.ctrl, self.world, self.seq, timeout_ms)
+
+    # -- static deal ----------------------------------------------------------------------------------
     def complete(self):
-        """All ranks' stores are in rank 0's memory once this returns on rank 0's stream."""
+        """Static deal: all ranks' stores are in rank 0's memory once this returns.  The renderer may launch on its
+        own non-blocking stream, which a NCCL barrier does not order after: synchronise it first."""
         import torch.distributed as dist
+        self.sr.sync()
         if self.world > 1:
             dist.barrier()
 
@@ -166,10 +193,17 @@ class SharedFrame:
         return torch.as_tensor(w, device="cuda")
 
     def close(self):
+        """Importers close their mapping first; only then does rank 0 free the exported allocation (freeing exported
+        memory that is still mapped elsewhere is undefined behaviour)."""
+        import torch.distributed as dist
+        self.sr.sync()
+        if self.rank != 0 and self.world > 1:
+            self.sr.sharedClose(self.ptr)
+        if self.world > 1:
+            dist.barrier()
         if self.rank == 0:
             self.sr.sharedFree(self.ptr)
-        elif self.world > 1:
-            self.sr.sharedClose(self.ptr)
+        self.ptr = None
 
 
 class SharedHostFrame:
@@ -197,7 +231,17 @@ class SharedHostFrame:
                 except Exception:
                     pass
         self.host_ptr = C.addressof(C.c_char.from_buffer(self.shm.buf))
-        self.ptr = sr.hostRegister(self.host_ptr, n_words * 4)
+        try:
+            self.ptr = sr.hostRegister(self.host_ptr, n_words * 4)
+        except BaseException:                # do not leak the /dev/shm segment: this object is never returned
+            self.host_ptr = None
+            try:
+                self.shm.close()
+            except BufferError:
+                pass
+            if rank == 0:
+                self.shm.unlink()
+            raise
 
     def complete(self):
         """Every rank: its kernel has finished (stream synchronised) and so have all the others'."""

@@ -137,3 +137,104 @@ def test_host_registered_frame_buffer(sr, R, oracle_envs):
     finally:
         sr.hostUnregister(buf.ctypes.data)
     assert np.array_equal(buf, want)
+
+
+def _view_i32(ptr, n):
+    import torch
+
+    class _W:
+        pass
+    w = _W()
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(w, device="cuda:0")
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
+    """include/rmdf.h rmdf_frame_begin / rmdf_frame_end (csrc/frame_sync.cuh): `world` contexts on ONE device play
+    the ranks of a multi-GPU frame — one control block, one frame buffer, every context launches the SAME full-frame
+    work list, the kernels (concurrent, on their own streams) claim items from the one queue, the last CTA of each
+    publishes the frame number, rank 0's stream waits for all arrival flags.  The frame must be bit-identical to a
+    plain render, every sample rendered exactly once, for consecutive frames and for the Julia kernel too."""
+    import torch
+    w, h, k = 1024, 512, 1
+    n_out = (w >> k) * (h >> k)
+    srs = [R.ShaderRenderer(0) for _ in range(world)]
+    try:
+        for r in srs:
+            for s in range(5):
+                r.bindCubeMap(s, oracle_envs[s])
+        want = srs[0].drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+        frame_bytes = (n_out * 4 + 255) & ~255
+        ptr, _ = srs[0].sharedAlloc(frame_bytes + 64 * 4)
+        ctrl = ptr + frame_bytes
+        p = srs[0].makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+        for seq in (1, 2, 3):
+            _view_i32(ptr, n_out).zero_(); torch.cuda.synchronize()
+            for r in srs:
+                r.resetCounters()
+            for rank in reversed(range(world)):               # the waiting ranks first: rank 0's "go" must still get through
+                srs[rank].frameBegin(ctrl, rank, world, seq, 5000)
+                srs[rank].renderDevice(p, ptr)
+            srs[0].frameEnd(ctrl, world, seq, 5000)
+            assert srs[0].frameSyncStatus() == 0              # synchronises rank 0's stream: the frame is complete
+            got = _view_i32(ptr, n_out).cpu().numpy().view(np.uint32).reshape(h >> k, w >> k)
+            assert np.array_equal(got, want), seq
+            for r in srs[1:]:
+                assert r.frameSyncStatus() == 0
+            assert sum(r.counters()["samples"] for r in srs) == w * h          # every sample exactly once
+        # Julia through the same protocol
+        jw, jh = 2048, 1024
+        wantj = srs[0].juliaAnimated(jw, jh, None, False, 7.0, resolve_log2=k)
+        for rank in reversed(range(world)):
+            srs[rank].frameBegin(ctrl, rank, world, 4, 5000)
+            srs[rank].juliaDevice(jw, jh, False, 7.0, (0, jh), k, ptr)
+        srs[0].frameEnd(ctrl, world, 4, 5000)
+        assert srs[0].frameSyncStatus() == 0
+        gotj = _view_i32(ptr, (jw >> k) * (jh >> k)).cpu().numpy().view(np.uint32).reshape(jh >> k, jw >> k)
+        assert np.array_equal(gotj, wantj)
+        # a tile / shard / packed layout cannot be combined with the shared queue
+        srs[0].frameBegin(ctrl, 0, 1, 5, 1000)
+        with pytest.raises(R.RmdfError):
+            srs[0].renderDevice(srs[0].makeParams(R.FragmentShader.FSMBPower8Shader, 3, w, h, 0.0), ptr)
+        srs[0].renderDevice(p, ptr); srs[0].frameEnd(ctrl, 1, 5, 1000)
+        assert srs[0].frameSyncStatus() == 0
+        # a wait that cannot be satisfied gives up after its timeout and says which word it waited for
+        srs[0].frameEnd(ctrl, 2, 99, 50)
+        assert srs[0].frameSyncStatus() in (1, 2)
+        for r in srs:
+            r.sync()
+        srs[0].sharedFree(ptr)
+    finally:
+        for r in srs:
+            r.close()
+
+
+def test_shared_queue_frame_two_gpus(R, oracle_envs):
+    """The same protocol across two devices over peer memory (single process; run with gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w, h, k = 2048, 1024, 2
+    n_out = (w >> k) * (h >> k)
+    with R.ShaderRenderer(0) as a, R.ShaderRenderer(1) as b:
+        for r in (a, b):
+            for s in range(5):
+                r.bindCubeMap(s, oracle_envs[s])
+        b.enablePeer(0)
+        want = a.drawShaderTile(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+        frame_bytes = (n_out * 4 + 255) & ~255
+        ptr, _ = a.sharedAlloc(frame_bytes + 64 * 4)
+        ctrl = ptr + frame_bytes
+        p = a.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
+        for seq in (1, 2):
+            a.resetCounters(); b.resetCounters()
+            b.frameBegin(ctrl, 1, 2, seq, 5000); b.renderDevice(p, ptr)
+            a.frameBegin(ctrl, 0, 2, seq, 5000); a.renderDevice(p, ptr)
+            a.frameEnd(ctrl, 2, seq, 5000)
+            assert a.frameSyncStatus() == 0 and b.frameSyncStatus() == 0
+            got = _view_i32(ptr, n_out).cpu().numpy().view(np.uint32).reshape(h >> k, w >> k)
+            assert np.array_equal(got, want)
+            ca, cb = a.counters()["samples"], b.counters()["samples"]
+            assert ca + cb == w * h and ca > 0 and cb > 0
+        a.sharedFree(ptr)

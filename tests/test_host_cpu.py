@@ -88,12 +88,20 @@ def test_output_sizing_and_validation(R):
     assert n(tile_idx=5) == 256 * 128 and nt.value == 1                     # frame layout: untouched pixels stay
     assert n(tile_idx=5, layout=R.LAYOUT_PACKED_TILES) == 32 * 16
     assert n(tile_idx=69, layout=R.LAYOUT_PACKED_TILES) == 32 * 16          # idx mod 64
+    # any frame size (ShaderRendering.hs:183-195): a pixel belongs to the tile that contains its centre
+    edge = lambda t, dim: (2 * t * dim + 7) >> 4
+    tot = 0
+    for idx in range(64):
+        v = n(fb_w=100, fb_h=45, tile_idx=idx, layout=R.LAYOUT_PACKED_TILES)
+        assert v == (edge(idx % 8 + 1, 100) - edge(idx % 8, 100)) * (edge(idx // 8 + 1, 45) - edge(idx // 8, 45))
+        tot += v
+    assert tot == 100 * 45 and n(fb_w=100, fb_h=45, tile_idx=3) == 100 * 45
     for g in (2, 4, 8):
         assert n(shard_count=g, shard_rank=g - 1, layout=R.LAYOUT_PACKED_TILES, resolve_log2=1) == (64 // g) * 16 * 8
         assert nt.value == 64 // g
     # errors: every one sets rmdf_last_error
     for bad in (dict(scene=4), dict(fb_w=0), dict(resolve_log2=4), dict(out_format=2), dict(mode=7), dict(lod_policy=3),
-                dict(out_format=R.OUT_RGBA32F, resolve_log2=1), dict(fb_w=250, resolve_log2=2), dict(fb_w=100, fb_h=100, tile_idx=0),
+                dict(out_format=R.OUT_RGBA32F, resolve_log2=1), dict(fb_w=250, resolve_log2=2), dict(fb_w=100, fb_h=100, tile_idx=1, resolve_log2=1),
                 dict(shard_count=2, shard_rank=2), dict(layout=R.LAYOUT_PACKED_TILES), dict(shard_count=3, shard_rank=0),
                 dict(shard_count=2, tile_idx=1), dict(shard_count=2, shard_grid_x=7, shard_grid_y=8), dict(shard_count=2, shard_grid_x=64, shard_grid_y=8, fb_w=320)):
         assert n(**bad) == -1, bad

@@ -96,6 +96,36 @@ def test_tiles_compose_to_full_frame(sr, O, R, oracle_envs):
     assert np.array_equal(fb, full)
 
 
+@pytest.mark.parametrize("size", [(100, 100), (67, 45), (5, 3), (250, 131)])
+def test_tiles_of_any_frame_size(sr, O, R, oracle_envs, size):
+    """ShaderRendering.hs:183-195 cuts ANY frame into 8×8 NDC rectangles; a pixel belongs to the tile that contains
+    its centre.  Tiles with odd edges split 2×2 fragment quads: GL shades such a quad whole (helper invocations), so
+    the min/mag decision — and every pixel — equals the full-frame draw.  Tile by tile against oracle.render(rect=…),
+    frame layout and packed layout, RGBA8 and linear output; the 64 tiles partition the frame."""
+    _bind(sr, oracle_envs)
+    w, h = size
+    edge = lambda t, dim: (2 * t * dim + 7) >> 4
+    full = O.render(1, w, h, 3.0, envs=oracle_envs)
+    acc = np.full((h, w), 0xDEADBEEF, np.uint32)
+    covered = np.zeros((h, w), np.int32)
+    for idx in range(64):
+        tx, ty = idx % 8, idx // 8
+        x0, x1, y0, y1 = edge(tx, w), edge(tx + 1, w), edge(ty, h), edge(ty + 1, h)
+        sr.drawShaderTile(R.FragmentShader.FSDETestShader, idx, w, h, 3.0, fb=acc)
+        covered[y0:y1, x0:x1] += 1
+        if x1 > x0 and y1 > y0:
+            ref = O.render(1, w, h, 3.0, envs=oracle_envs, rect=(x0, y0, x1, y1))
+            assert np.array_equal(ref["fb"], full["fb"][y0:y1, x0:x1])                 # the oracle itself: tiling does not change a pixel
+            assert np.array_equal(acc[y0:y1, x0:x1], ref["fb"]), (idx, x0, x1, y0, y1)
+            packed = sr.drawShaderTile(R.FragmentShader.FSDETestShader, idx, w, h, 3.0, layout=R.LAYOUT_PACKED_TILES)
+            assert packed.size == (x1 - x0) * (y1 - y0) and np.array_equal(packed.reshape(y1 - y0, x1 - x0), ref["fb"])
+            if idx in (0, 9, 27, 63):
+                lin = sr.drawShaderTile(R.FragmentShader.FSDETestShader, idx, w, h, 3.0, layout=R.LAYOUT_PACKED_TILES, out_format=R.OUT_RGBA32F)
+                assert np.array_equal(lin.reshape(y1 - y0, x1 - x0, 4)[..., :3].view(np.uint32), ref["linear"].view(np.uint32))
+    assert (covered == 1).all()
+    assert np.array_equal(acc, full["fb"])
+
+
 @pytest.mark.parametrize("k", [1, 2, 3])
 def test_in_kernel_resolve_equals_mip_chain(sr, O, R, oracle_envs, k):
     """spp = 4^k: the kernel's in-register/shared resolve == glGenerateMipmap level k of level 0."""
@@ -264,8 +294,6 @@ def test_cornell_exact_culling(sr, O, R, oracle_envs, time, flags):
 def test_error_behaviour(sr, R):
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(5, None, 64, 64, 0.0)
-    with pytest.raises(R.RmdfError):
-        sr.drawShaderTile(R.FragmentShader.FSDETestShader, 3, 100, 100, 0.0)      # tiles need /16
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(R.FragmentShader.FSDETestShader, None, 66, 64, 0.0, resolve_log2=2)
     with pytest.raises(R.RmdfError):
