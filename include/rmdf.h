@@ -69,7 +69,13 @@ enum { RMDF_LOD_QUAD = 0,      /* min=NEAREST/mag=LINEAR per 2×2 quad (GLHelper
  * Each is bit-identical to the oracle with the same switch; none changes the default path. */
 enum { RMDF_FLAG_NORMAL_CENTRAL = 1,    /* normal_central_difference (fragment.shd:471-480) instead of :463-470 */
        RMDF_FLAG_CAM_ORTHO = 2,         /* #define CAM_ORTHO (fragment.shd:906-908, 853-861), width 2 */
-       RMDF_FLAG_RAY_TRACING_TEST = 4 };/* #define RAY_TRACING_TEST (fragment.shd:915-937): ray-traced Cornell box */
+       RMDF_FLAG_RAY_TRACING_TEST = 4, /* #define RAY_TRACING_TEST (fragment.shd:915-937): ray-traced Cornell box */
+       /* NOT IN THE REFERENCE (fragment.shd has no shadow code): BASELINE.json's north_star names soft
+        * shadows, so they exist as an opt-in that is off by default and excluded from every parity statement.  A
+        * distance-field penumbra march (Quilez: res = min(res, k·d/t), k = 8, ≤ 48 steps) from the hit point towards
+        * the fixed light normalize(1,1,1) of the shader's commented-out soft_lam call (:778); scales the diffuse and
+        * specular terms of :805-810 by the result.  Hit/miss masks and miss pixels are unchanged. */
+       RMDF_FLAG_SOFT_SHADOWS = 8 };
 enum { RMDF_LAYOUT_FRAME = 0,  /* output indexed px + py·w over the whole frame          */
        RMDF_LAYOUT_PACKED_TILES = 1 }; /* the rendered tiles back to back, ascending (ty, tx) */
 
@@ -80,6 +86,10 @@ int  rmdf_create(rmdf_ctx **out, int device);
 void rmdf_destroy(rmdf_ctx *ctx);
 /* `Either String`: message of the last failing call on this thread ("" if none). */
 const char *rmdf_last_error(void);
+/* The same for the last failing call ON THIS CONTEXT, copied into buf (NUL-terminated, at most cap bytes), whatever
+ * OS thread made that call: under GHC -threaded an unbound Haskell thread may run two consecutive `safe` foreign
+ * calls on different OS threads, so the shim (haskell/RMDF/FFI.hs `check`) fetches the message through the context. */
+int  rmdf_ctx_last_error(rmdf_ctx *ctx, char *buf, int cap);
 int  rmdf_abi_version(void);
 /* Run on the caller's CUDA stream (cudaStream_t) instead of the context's own;
  * NULL restores the private stream.  Lets a host time with its own events. */

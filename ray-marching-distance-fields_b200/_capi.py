@@ -17,10 +17,10 @@ MODE_PARITY, MODE_FAST = 0, 1
 OUT_RGBA8, OUT_RGBA32F = 0, 1
 LOD_QUAD, LOD_ALWAYS_LINEAR = 0, 1
 LAYOUT_FRAME, LAYOUT_PACKED_TILES = 0, 1
-FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST = 1, 2, 4
+FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST, FLAG_SOFT_SHADOWS = 1, 2, 4, 8
 
 EXPORTS = [
-    "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
+    "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_ctx_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
     "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device", "rmdf_envmap_convolve_rows_device",
     "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_bind_cubes", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
@@ -77,6 +77,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_destroy.argtypes = [vp]; L.rmdf_destroy.restype = None
     L.rmdf_last_error.argtypes = []; L.rmdf_last_error.restype = C.c_char_p
     L.rmdf_abi_version.argtypes = []
+    L.rmdf_ctx_last_error.argtypes = [vp, C.c_char_p, C.c_int]
     L.rmdf_set_stream.argtypes = [vp, vp]
     L.rmdf_sync.argtypes = [vp]
     L.rmdf_envmap_resize_height.argtypes = [C.c_int] * 3

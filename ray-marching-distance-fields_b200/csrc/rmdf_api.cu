@@ -20,6 +20,7 @@ using namespace rmdf;
 
 // ---------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static thread_local bool g_err_fresh = false;       // set by fail(); a DeviceGuard copies the message into its context
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -27,6 +28,7 @@ static int fail(int code, const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+    g_err_fresh = true;
     return code;
 }
 #define CU(call)                                                                                   \
@@ -62,6 +64,11 @@ struct rmdf_ctx {
     void *d_out = nullptr;             // staging for the host-pointer entry points
     size_t d_out_bytes = 0;
     std::recursive_mutex mu;
+    // message of the last failing call on THIS context, whatever OS thread made it (rmdf_ctx_last_error): a Haskell
+    // `safe` foreign call may run the call and the error fetch on different OS threads, where the thread-local
+    // rmdf_last_error() would be empty or stale
+    std::mutex err_mu;
+    char last_err[512] = "";
 };
 
 // Every entry point runs on ctx's device and puts the caller's current device back on return: a host
@@ -69,9 +76,12 @@ struct rmdf_ctx {
 struct DeviceGuard {
     int prev = -1;
     bool changed = false;
+    rmdf_ctx *owner = nullptr;
     int enter(rmdf_ctx *ctx)
     {
         if (!ctx) return fail(RMDF_ERR_ARG, "ctx is NULL");
+        owner = ctx;
+        g_err_fresh = false;
         if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
         if (prev != ctx->device) {
             CU(cudaSetDevice(ctx->device));
@@ -79,7 +89,14 @@ struct DeviceGuard {
         }
         return RMDF_OK;
     }
-    ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard()
+    {
+        if (owner && g_err_fresh) {
+            std::lock_guard<std::mutex> lk(owner->err_mu);
+            memcpy(owner->last_err, g_err, sizeof g_err);
+        }
+        if (changed && prev >= 0) cudaSetDevice(prev);
+    }
 };
 static int ensure_staging(rmdf_ctx *ctx, size_t bytes)
 {
@@ -92,6 +109,13 @@ static int ensure_staging(rmdf_ctx *ctx, size_t bytes)
 
 // ---------------------------------------------------------------------------------
 extern "C" const char *rmdf_last_error(void) { return g_err; }
+extern "C" int rmdf_ctx_last_error(rmdf_ctx *ctx, char *buf, int cap)
+{
+    if (!ctx || !buf || cap < 1) return RMDF_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    snprintf(buf, (size_t)cap, "%s", ctx->last_err);
+    return RMDF_OK;
+}
 extern "C" int rmdf_abi_version(void) { return RMDF_ABI_VERSION; }
 
 extern "C" int rmdf_create(rmdf_ctx **out, int device)
@@ -522,7 +546,7 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     if (p->mode != RMDF_MODE_PARITY && p->mode != RMDF_MODE_FAST) return fail(RMDF_ERR_ARG, "mode %d unknown", p->mode);
     if (p->lod_policy != RMDF_LOD_QUAD && p->lod_policy != RMDF_LOD_ALWAYS_LINEAR) return fail(RMDF_ERR_ARG, "lod_policy %d unknown", p->lod_policy);
     if (p->layout != RMDF_LAYOUT_FRAME && p->layout != RMDF_LAYOUT_PACKED_TILES) return fail(RMDF_ERR_ARG, "layout %d unknown", p->layout);
-    if (p->flags & ~(RMDF_FLAG_NORMAL_CENTRAL | RMDF_FLAG_CAM_ORTHO | RMDF_FLAG_RAY_TRACING_TEST)) return fail(RMDF_ERR_ARG, "unknown bits in flags: 0x%x", p->flags);
+    if (p->flags & ~(RMDF_FLAG_NORMAL_CENTRAL | RMDF_FLAG_CAM_ORTHO | RMDF_FLAG_RAY_TRACING_TEST | RMDF_FLAG_SOFT_SHADOWS)) return fail(RMDF_ERR_ARG, "unknown bits in flags: 0x%x", p->flags);
     const int k = p->resolve_log2, q = 1 << k;
     const bool sharded = p->shard_count > 1;
     if (sharded && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return fail(RMDF_ERR_ARG, "shard_rank %d not in [0,%d)", p->shard_rank, p->shard_count);

@@ -22,6 +22,7 @@ module RMDF.FFI
     , rmdfJulia
     ) where
 
+import Control.Concurrent (runInBoundThread)
 import Control.Exception (bracket)
 import Control.Monad (when)
 import Data.Int
@@ -45,6 +46,7 @@ data FragmentShader = FSDECornellBoxShader | FSDETestShader | FSMBPower8Shader |
 foreign import ccall safe "rmdf_create"            c_create     :: Ptr RmdfCtx -> CInt -> IO CInt
 foreign import ccall safe "rmdf_destroy"           c_destroy    :: RmdfCtx -> IO ()
 foreign import ccall safe "rmdf_last_error"        c_last_error :: IO CString
+foreign import ccall safe "rmdf_ctx_last_error"    c_ctx_last_error :: RmdfCtx -> CString -> CInt -> IO CInt
 foreign import ccall safe "rmdf_render"            c_render     :: RmdfCtx -> Ptr RmdfParams -> Ptr Word32 -> IO CInt
 foreign import ccall safe "rmdf_envmap_convolve"   c_convolve   :: RmdfCtx -> Ptr CFloat -> CInt -> CInt -> Ptr CFloat -> CInt -> Ptr CFloat -> IO CInt
 foreign import ccall safe "rmdf_envmap_resize"     c_resize     :: RmdfCtx -> Ptr CFloat -> CInt -> CInt -> CInt -> Ptr CFloat -> IO CInt
@@ -73,9 +75,19 @@ instance Storable RmdfParams where
         mapM_ (\off -> i off 0) [48, 52, 56, 60, 64, 68]            -- shard_grid_x/y, shard_skew (0 = 8×8 grid), flags (0 = the reference's build), row_begin/row_end (0,0 = all rows)
 
 -- | `Left <message>` like the ExceptT String the reference threads through withShaderRenderer.
+--   The message comes through the context (rmdf_ctx_last_error): under -threaded an unbound Haskell thread may run
+--   the failing `safe` call and the fetch on different OS threads, where the thread-local rmdf_last_error is stale.
+checkCtx :: RmdfCtx -> CInt -> IO (Either String ())
+checkCtx _   0 = return $ Right ()
+checkCtx ctx _ = allocaBytes 512 $ \buf -> c_ctx_last_error ctx buf 512 >> (Left <$> peekCString buf)
+
+-- | For the calls that have no context yet (rmdf_create, rmdf_cornell_box_vertices): call and fetch on ONE OS thread.
 check :: CInt -> IO (Either String ())
 check 0 = return $ Right ()
 check _ = Left <$> (c_last_error >>= peekCString)
+
+orThrowBound :: IO CInt -> IO ()
+orThrowBound act = runInBoundThread (act >>= check) >>= either (ioError . userError) return
 
 orThrow :: IO CInt -> IO ()
 orThrow act = act >>= check >>= either (ioError . userError) return
@@ -85,11 +97,11 @@ orThrow act = act >>= check >>= either (ioError . userError) return
 withRmdf :: Int -> (RmdfCtx -> IO a) -> IO a
 withRmdf device = bracket create c_destroy
   where create = alloca $ \pp -> do
-            orThrow $ c_create pp (fromIntegral device)
+            orThrowBound $ c_create pp (fromIntegral device)
             ctx <- peek pp
             allocaArray 288 $ \xyz -> do
-                orThrow $ c_cornell xyz
-                orThrow $ c_set_cornell ctx xyz 96
+                orThrowBound $ c_cornell xyz
+                c_set_cornell ctx xyz 96 >>= checkCtx ctx >>= either (ioError . userError) return
             return ctx
 
 -- | The body of drawShaderTile (ShaderRendering.hs:151-196) for a frame buffer handed out by
@@ -106,7 +118,7 @@ rmdfRenderTile ctx shd tileIdx w h time fb
                                , pTileIdx = maybe (-1) fromIntegral tileIdx
                                , pResolveLog2 = 0, pOutFormat = 0, pMode = 0, pLodPolicy = 0
                                , pShardRank = 0, pShardCount = 1, pLayout = 0 }
-            VSM.unsafeWith fb $ \p -> c_render ctx pp p >>= check
+            VSM.unsafeWith fb $ \p -> c_render ctx pp p >>= checkCtx ctx
 
 -- | cosineConvolveHDREnvMap (HDREnvMap.hs:217-254) for all powers at once; images are the
 --   interleaved-RGB `VS.Vector Float` of JuicyPixels' `Image PixelRGBF` (imageData).
@@ -116,7 +128,7 @@ rmdfConvolve ctx src w h powers = do
     out <- VSM.new (n * length powers)
     r <- VS.unsafeWith src $ \ps -> withArrayLen (map realToFrac powers) $ \np pp ->
            VSM.unsafeWith out $ \po ->
-             c_convolve ctx (castPtr ps) (fromIntegral w) (fromIntegral h) pp (fromIntegral np) (castPtr po) >>= check
+             c_convolve ctx (castPtr ps) (fromIntegral w) (fromIntegral h) pp (fromIntegral np) (castPtr po) >>= checkCtx ctx
     frozen <- VS.unsafeFreeze out
     return $ fmap (const [VS.slice (i * n) n frozen | i <- [0 .. length powers - 1]]) r
 
@@ -126,7 +138,7 @@ rmdfResize ctx src w h dstw = do
     dsth <- fromIntegral <$> c_resize_h (fromIntegral w) (fromIntegral h) (fromIntegral dstw)
     out  <- VSM.new (dstw * dsth * 3)
     r <- VS.unsafeWith src $ \ps -> VSM.unsafeWith out $ \po ->
-           c_resize ctx (castPtr ps) (fromIntegral w) (fromIntegral h) (fromIntegral dstw) (castPtr po) >>= check
+           c_resize ctx (castPtr ps) (fromIntegral w) (fromIntegral h) (fromIntegral dstw) (castPtr po) >>= checkCtx ctx
     frozen <- VS.unsafeFreeze out
     return $ fmap (const (dsth, frozen)) r
 
@@ -134,7 +146,7 @@ rmdfResize ctx src w h dstw = do
 --   slot 0..4 = env_reflection, env_cos_1, env_cos_8, env_cos_64, env_cos_512.
 rmdfBindLatLong :: RmdfCtx -> Int -> VS.Vector Float -> Int -> Int -> IO (Either String ())
 rmdfBindLatLong ctx slot img w h =
-    VS.unsafeWith img $ \p -> c_bind ctx (fromIntegral slot) (castPtr p) (fromIntegral w) (fromIntegral h) >>= check
+    VS.unsafeWith img $ \p -> c_bind ctx (fromIntegral slot) (castPtr p) (fromIntegral w) (fromIntegral h) >>= checkCtx ctx
 
 -- | juliaAnimated (Fractal2D.hs:63-98) into a fillFrameBuffer vector.
 rmdfJulia :: RmdfCtx -> Int -> Int -> VSM.IOVector Word32 -> Bool -> Double -> IO (Either String ())
@@ -142,4 +154,4 @@ rmdfJulia ctx w h fb smooth tick = do
     when (VSM.length fb < w * h) $ ioError (userError "rmdfJulia: frame buffer too small")
     VSM.unsafeWith fb $ \p ->
         c_julia ctx (fromIntegral w) (fromIntegral h) (if smooth then 1 else 0) (realToFrac tick)
-                0 (fromIntegral h) 0 p >>= check
+                0 (fromIntegral h) 0 p >>= checkCtx ctx

@@ -238,3 +238,23 @@ def test_shared_queue_frame_two_gpus(R, oracle_envs):
             ca, cb = a.counters()["samples"], b.counters()["samples"]
             assert ca + cb == w * h and ca > 0 and cb > 0
         a.sharedFree(ptr)
+
+
+def test_error_message_through_the_context_from_another_thread(sr, R):
+    """rmdf_ctx_last_error: the message of a failing call is readable from ANY OS thread (a Haskell `safe` foreign
+    call may run the call and the fetch on different threads); the thread-local rmdf_last_error is empty there."""
+    import threading
+    p = sr.makeParams(R.FragmentShader.FSDETestShader, None, 64, 64, 0.0, resolve_log2=5)
+    assert sr._lib.rmdf_render_device(sr.handle, C.byref(p), C.c_void_p(16)) == R._capi.ERR_ARG
+    got = {}
+
+    def fetch():
+        buf = C.create_string_buffer(512)
+        got["rc"] = sr._lib.rmdf_ctx_last_error(sr.handle, buf, 512)
+        got["ctx"] = buf.value.decode()
+        got["tls"] = sr._lib.rmdf_last_error().decode()
+    t = threading.Thread(target=fetch); t.start(); t.join()
+    assert got["rc"] == 0 and "resolve_log2" in got["ctx"] and got["tls"] == ""
+    # the caller's current device is what it was (DeviceGuard)
+    import torch
+    assert torch.cuda.current_device() == 0

@@ -108,7 +108,7 @@ def test_output_sizing_and_validation(R):
         assert len(L.rmdf_last_error()) > 0
     assert n(shard_count=4, shard_rank=1, shard_grid_x=32, shard_grid_y=16, shard_skew=2, layout=R.LAYOUT_PACKED_TILES) == 256 * 128 // 4
     assert nt.value == 32 * 16 // 4
-    p = _params(R); p.flags = 8
+    p = _params(R); p.flags = 16
     assert L.rmdf_render_output_pixels(C.byref(p), None) == -1
     assert L.rmdf_render_output_pixels(None, None) == -1
 

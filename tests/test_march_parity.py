@@ -291,6 +291,30 @@ def test_cornell_exact_culling(sr, O, R, oracle_envs, time, flags):
     assert agree >= 0.999 and p >= 35.0
 
 
+@pytest.mark.parametrize("scene", [0, 1, 2])
+def test_soft_shadows_opt_in_not_parity(sr, O, R, oracle_envs, scene):
+    """RMDF_FLAG_SOFT_SHADOWS: NOT in the reference (fragment.shd has no shadow code); north_star names
+    soft shadows, so they are an opt-in, default off, excluded from parity.  Checked here: without the flag nothing
+    changes (the default path equals the oracle), with it the hit mask and every miss pixel stay what they were, hit
+    pixels only get darker (some strictly), and the result is deterministic."""
+    _bind(sr, oracle_envs)
+    w, h = 256, 160
+    ref = O.render(scene, w, h, 0.0, envs=oracle_envs)
+    base = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 0.0, out_format=R.OUT_RGBA32F)
+    assert np.array_equal(base[..., :3].view(np.uint32), ref["linear"].view(np.uint32))
+    for mode in (R.MODE_PARITY, R.MODE_FAST):
+        plain = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 0.0, out_format=R.OUT_RGBA32F, mode=mode)
+        sh = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 0.0, out_format=R.OUT_RGBA32F, mode=mode, flags=R.FLAG_SOFT_SHADOWS)
+        again = sr.drawShaderTile(R.FragmentShader(scene), None, w, h, 0.0, out_format=R.OUT_RGBA32F, mode=mode, flags=R.FLAG_SOFT_SHADOWS)
+        assert np.array_equal(sh.view(np.uint32), again.view(np.uint32))
+        hit = plain[..., 3] > 0.5
+        assert np.array_equal(sh[..., 3] > 0.5, hit)
+        assert np.array_equal(sh[~hit].view(np.uint32), plain[~hit].view(np.uint32))
+        a, b = np.nan_to_num(sh[hit][:, :3]), np.nan_to_num(plain[hit][:, :3])
+        assert (a <= b * 1.000001 + 1e-7).all()
+        assert (a < b * 0.99).mean() > 0.02, "no pixel is in shadow"
+
+
 def test_error_behaviour(sr, R):
     with pytest.raises(R.RmdfError):
         sr.drawShaderTile(5, None, 64, 64, 0.0)
