@@ -28,100 +28,129 @@
 #include <mutex>
 #include <vector>
 #include "rmdf_internal.h"
+#include "packed_f32.cuh"
 
 namespace rmdf {
 
 constexpr int CV_DX = 32, CV_DY = 8, CV_THREADS = CV_DX * CV_DY;
+constexpr int CV_SEGS = 3;             // a CTA's unit range touches at most this many destination tiles (see launch_convolve)
 
+// Work decomposition.  The sweep is tiles × h "row units": destination tile t (32×8 pixels) against source row y.
+// The grid is a whole number of CTAs per SM and CTA c owns the contiguous unit range [c·U/C, (c+1)·U/C) of the
+// tile-major list — every CTA gets the same amount of work to within one source row (round 1 launched 512 equal
+// CTAs on 148 SMs: 3 or 4 per SM, i.e. 86 % balance).  A range that crosses a tile boundary is processed as two
+// segments; each segment writes one partial sum per destination pixel and the finish kernel adds a pixel's partials
+// in ascending CTA order (deterministic, no float atomics).
+//
 // tab: [dst_w][src_w] cos|φ_L − φ_x| ; cth/sth: cos/sin θ per row (host, libm)
-// partial: [splits][h*w][13]  (4 powers × rgb, n)
+// partial: [C·CV_SEGS][CV_THREADS][13]  (4 powers × rgb, n)
 template <bool CHAIN>
 __global__ void __launch_bounds__(CV_THREADS)
 convolve_kernel(const float *__restrict__ src, int w, int h, const float *__restrict__ tab,
                 const float *__restrict__ cth, const float *__restrict__ sth,
-                float p0, float p1, float p2, float p3, int np, int rows_per_split,
-                int dst_y0, int dst_y1, float *__restrict__ partial)
+                float p0, float p1, float p2, float p3, int np,
+                int dst_y0, int dst_y1, int tiles_x, long long units, float *__restrict__ partial)
 {
     extern __shared__ float smem[];
     float *s_tab = smem;                                  // [w][CV_DX]  (transposed slice)
     float4 *s_row = reinterpret_cast<float4 *>(smem + (size_t)w * CV_DX);   // [2][w]
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int dstx = blockIdx.x * CV_DX + tx, dsty = dst_y0 + blockIdx.y * CV_DY + ty;       // destination rows [dst_y0, dst_y1)
-    const bool valid = dstx < w && dsty < dst_y1;
+    long long u = (long long)blockIdx.x * units / gridDim.x;
+    const long long u1 = (long long)(blockIdx.x + 1) * units / gridDim.x;
+    int loaded_tx = -1;
 
-    for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) {
-        const int sx = i / CV_DX, dx = blockIdx.x * CV_DX + (i % CV_DX);
-        s_tab[i] = (dx < w) ? tab[(size_t)dx * w + sx] : 0.0f;
-    }
-    const float lobe_cos = valid ? cth[dsty] : 0.0f, lobe_sin = valid ? sth[dsty] : 0.0f;
-    float acc[4][3];
-#pragma unroll
-    for (int p = 0; p < 4; p++) acc[p][0] = acc[p][1] = acc[p][2] = 0.0f;
-    float n = 0.0f;
-
-    const int y_begin = blockIdx.z * rows_per_split, y_end = min(h, y_begin + rows_per_split);
-    for (int y = y_begin; y < y_end; y++) {
-        float4 *row = s_row + (size_t)((y - y_begin) & 1) * w;
-        const float ps = sth[y];
-        for (int i = threadIdx.x; i < w; i += CV_THREADS) {
-            const float *s = src + ((size_t)y * w + i) * 3;
-            row[i] = make_float4(s[0] * ps, s[1] * ps, s[2] * ps, 0.0f);
+    for (int seg = 0; u < u1; seg++) {
+        const int tile = (int)(u / h), y_begin = (int)(u - (long long)tile * h);
+        const int y_end = (int)min((long long)h, y_begin + (u1 - u));
+        const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+        const int dstx = tile_x * CV_DX + tx, dsty = dst_y0 + tile_y * CV_DY + ty;       // destination rows [dst_y0, dst_y1)
+        const bool valid = dstx < w && dsty < dst_y1;
+        __syncthreads();                                   // the previous segment is done with s_tab / s_row
+        if (tile_x != loaded_tx) {
+            for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) {
+                const int sx = i / CV_DX, dx = tile_x * CV_DX + (i % CV_DX);
+                s_tab[i] = (dx < w) ? tab[(size_t)dx * w + sx] : 0.0f;
+            }
+            loaded_tx = tile_x;
         }
-        __syncthreads();                                   // double-buffered: one barrier per row
-        const float a = __fmul_rn(lobe_cos, cth[y]);       // thetaLobeCos * thetaPxCos
-        const float b = __fmul_rn(lobe_sin, ps);           // thetaLobeSin * thetaPxSin
-#pragma unroll 4
-        for (int x = 0; x < w; x++) {
-            // cosAngle, HDREnvMap.hs:242-244, same rounding sequence as the reference
-            const float c = __fadd_rn(a, __fmul_rn(b, s_tab[x * CV_DX + tx]));
-            const float4 px = row[x];
-            const bool pos = c > 0.0f;
-            const float cc = pos ? c : 0.0f;
-            n += pos ? 1.0f : 0.0f;
-            if (CHAIN) {                                   // powers 1, 8, 64, 512
-                const float c2 = cc * cc, c4 = c2 * c2, c8 = c4 * c4;
-                const float c16 = c8 * c8, c32 = c16 * c16, c64 = c32 * c32;
-                const float c128 = c64 * c64, c256 = c128 * c128, c512 = c256 * c256;
-                acc[0][0] = __fmaf_rn(px.x, cc, acc[0][0]);   acc[0][1] = __fmaf_rn(px.y, cc, acc[0][1]);   acc[0][2] = __fmaf_rn(px.z, cc, acc[0][2]);
-                acc[1][0] = __fmaf_rn(px.x, c8, acc[1][0]);   acc[1][1] = __fmaf_rn(px.y, c8, acc[1][1]);   acc[1][2] = __fmaf_rn(px.z, c8, acc[1][2]);
-                acc[2][0] = __fmaf_rn(px.x, c64, acc[2][0]);  acc[2][1] = __fmaf_rn(px.y, c64, acc[2][1]);  acc[2][2] = __fmaf_rn(px.z, c64, acc[2][2]);
-                acc[3][0] = __fmaf_rn(px.x, c512, acc[3][0]); acc[3][1] = __fmaf_rn(px.y, c512, acc[3][1]); acc[3][2] = __fmaf_rn(px.z, c512, acc[3][2]);
-            } else {
-                const float pw[4] = { p0, p1, p2, p3 };
+        const float lobe_cos = valid ? cth[dsty] : 0.0f, lobe_sin = valid ? sth[dsty] : 0.0f;
+        // accumulators: powers (1, 8) and (64, 512) side by side in 64-bit register pairs — one FFMA2 per channel and
+        // pair does two individually rounded FMAs in one issue slot (csrc/packed_f32.cuh); generic powers use .x/.y too
+        f2 a01[3], a23[3];
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    if (p < np) {
-                        const float cp = pos ? powf(c, pw[p]) : 0.0f;
-                        acc[p][0] = __fmaf_rn(px.x, cp, acc[p][0]);
-                        acc[p][1] = __fmaf_rn(px.y, cp, acc[p][1]);
-                        acc[p][2] = __fmaf_rn(px.z, cp, acc[p][2]);
-                    }
+        for (int ch = 0; ch < 3; ch++) { a01[ch] = F2(0.0f); a23[ch] = F2(0.0f); }
+        int n = 0;
+
+        for (int y = y_begin; y < y_end; y++) {
+            float4 *row = s_row + (size_t)((y - y_begin) & 1) * w;
+            const float ps = sth[y];
+            for (int i = threadIdx.x; i < w; i += CV_THREADS) {
+                const float *sp = src + ((size_t)y * w + i) * 3;
+                row[i] = make_float4(sp[0] * ps, sp[1] * ps, sp[2] * ps, 0.0f);
+            }
+            __syncthreads();                               // double-buffered: one barrier per row
+            const float a = __fmul_rn(lobe_cos, cth[y]);   // thetaLobeCos * thetaPxCos
+            const float b = __fmul_rn(lobe_sin, ps);       // thetaLobeSin * thetaPxSin
+#pragma unroll 4
+            for (int x = 0; x < w; x++) {
+                // cosAngle, HDREnvMap.hs:242-244, same rounding sequence as the reference
+                const float c = __fadd_rn(a, __fmul_rn(b, s_tab[x * CV_DX + tx]));
+                const float4 px = row[x];
+                const bool pos = c > 0.0f;
+                const float cc = fmaxf(c, 0.0f);
+                n += pos ? 1 : 0;
+                f2 q01, q23;
+                if (CHAIN) {                               // powers 1, 8, 64, 512 from nine squarings
+                    const float c2 = cc * cc, c4 = c2 * c2, c8 = c4 * c4;
+                    const float c16 = c8 * c8, c32 = c16 * c16, c64 = c32 * c32;
+                    const float c128 = c64 * c64, c256 = c128 * c128, c512 = c256 * c256;
+                    q01 = F2(cc, c8); q23 = F2(c64, c512);
+                } else {
+                    q01 = F2(pos ? powf(c, p0) : 0.0f, (np > 1 && pos) ? powf(c, p1) : 0.0f);
+                    q23 = F2((np > 2 && pos) ? powf(c, p2) : 0.0f, (np > 3 && pos) ? powf(c, p3) : 0.0f);
                 }
+                a01[0] = fma2(px.x, q01, a01[0]); a01[1] = fma2(px.y, q01, a01[1]); a01[2] = fma2(px.z, q01, a01[2]);
+                a23[0] = fma2(px.x, q23, a23[0]); a23[1] = fma2(px.y, q23, a23[1]); a23[2] = fma2(px.z, q23, a23[2]);
             }
         }
-    }
-    if (valid) {
-        float *o = partial + ((size_t)blockIdx.z * h * w + (size_t)dsty * w + dstx) * 13;
+        if (seg < CV_SEGS) {
+            float *o = partial + (((size_t)blockIdx.x * CV_SEGS + seg) * CV_THREADS + threadIdx.x) * 13;
 #pragma unroll
-        for (int p = 0; p < 4; p++) { o[p * 3] = acc[p][0]; o[p * 3 + 1] = acc[p][1]; o[p * 3 + 2] = acc[p][2]; }
-        o[12] = n;
+            for (int ch = 0; ch < 3; ch++) { o[ch] = a01[ch].x; o[3 + ch] = a01[ch].y; o[6 + ch] = a23[ch].x; o[9 + ch] = a23[ch].y; }
+            o[12] = (float)n;
+        }
+        u += y_end - y_begin;
     }
 }
 
-// out[p][y][x][c] = Σ_splits acc / Σ_splits n   ("divide sum by number of hemisphere samples", :231-232)
-__global__ void convolve_finish_kernel(const float *__restrict__ partial, int npix, int splits, int np, int i0, int i1, float *__restrict__ out)
+// out[p][y][x][c] = Σ_segments acc / Σ_segments n   ("divide sum by number of hemisphere samples", :231-232).
+// One thread per destination pixel; its segments are those of the CTAs whose unit range meets the pixel's tile.
+__global__ void convolve_finish_kernel(const float *__restrict__ partial, int w, int h, int npix, int np, int dst_y0, int dst_y1,
+                                       int tiles_x, long long units, int ctas, float *__restrict__ out)
 {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= i1) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = dst_y1 - dst_y0;
+    if (i >= rows * w) return;
+    const int dsty = dst_y0 + i / w, dstx = i % w;
+    const int tile = ((dsty - dst_y0) / CV_DY) * tiles_x + dstx / CV_DX;
+    const int t = ((dsty - dst_y0) % CV_DY) * CV_DX + (dstx % CV_DX);              // thread index inside the tile's CTA
+    const long long lo = (long long)tile * h, hi = lo + h;                         // the tile's units
     float acc[12], n = 0.0f;
     for (int k = 0; k < 12; k++) acc[k] = 0.0f;
-    for (int s = 0; s < splits; s++) {
-        const float *p = partial + ((size_t)s * npix + i) * 13;
+    int c = (int)(lo * ctas / units);                                              // a CTA at or just before the first owner
+    while (c > 0 && (long long)c * units / ctas > lo) c--;
+    for (; c < ctas; c++) {
+        const long long u0 = (long long)c * units / ctas, u1 = (long long)(c + 1) * units / ctas;
+        if (u1 <= lo) continue;
+        if (u0 >= hi) break;
+        const int seg = tile - (int)(u0 / h);                                      // 0 for the tile the range starts in
+        const float *p = partial + (((size_t)c * CV_SEGS + seg) * CV_THREADS + t) * 13;
         for (int k = 0; k < 12; k++) acc[k] += p[k];
         n += p[12];
     }
+    const size_t pix = (size_t)dsty * w + dstx;
     for (int p = 0; p < np; p++)
-        for (int c = 0; c < 3; c++) out[((size_t)p * npix + i) * 3 + c] = acc[p * 3 + c] / n;
+        for (int ch = 0; ch < 3; ch++) out[((size_t)p * npix + pix) * 3 + ch] = acc[p * 3 + ch] / n;
 }
 
 // Host-side tables, same libm calls and rounding as HDREnvMap.hs:223-236.
@@ -166,29 +195,39 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
         }
     }
     float *d_partial = nullptr;
-    const int splits = 4, rows_per_split = (h + splits - 1) / splits;
     const size_t npix = (size_t)w * h;
-    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * splits * npix * 13, s)) != cudaSuccess) return e;
+    const int tiles_x = (w + CV_DX - 1) / CV_DX, tiles_y = (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY;
+    const long long units = (long long)tiles_x * tiles_y * h;
     const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
-    const dim3 grid((w + CV_DX - 1) / CV_DX, (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY, splits);
+    // a whole number of CTAs per SM (as many as are resident), never so many that a unit range is shorter than h/2 rows
+    // (then a range meets at most CV_SEGS = 3 tiles) nor more than there are units
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(convolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, convolve_kernel<true>, CV_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long ctas = (long long)sms * per_sm;
+    while (ctas > sms && units / ctas < (h + 1) / 2) ctas -= sms;
+    if (units / ctas < (h + 1) / 2) ctas = units / ((h + 1) / 2) > 0 ? units / ((h + 1) / 2) : 1;
+    if (ctas > units) ctas = units;
+    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * (size_t)ctas * CV_SEGS * CV_THREADS * 13, s)) != cudaSuccess) return e;
     for (int first = 0; first < np && e == cudaSuccess; first += 4) {
         const int cnt = (np - first < 4) ? np - first : 4;
         float p[4] = { 0, 0, 0, 0 };
         for (int k = 0; k < cnt; k++) p[k] = powers_host[first + k];
         const bool chain = cnt == 4 && p[0] == 1.0f && p[1] == 8.0f && p[2] == 64.0f && p[3] == 512.0f;
-        if (chain) {
-            cudaFuncSetAttribute(convolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            convolve_kernel<true><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                 p[0], p[1], p[2], p[3], cnt, rows_per_split, dst_y0, dst_y1, d_partial);
-        } else {
-            cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            convolve_kernel<false><<<grid, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                  p[0], p[1], p[2], p[3], cnt, rows_per_split, dst_y0, dst_y1, d_partial);
-        }
+        if (chain)
+            convolve_kernel<true><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
+                                                                          p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, d_partial);
+        else
+            convolve_kernel<false><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
+                                                                           p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, d_partial);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
-        const int i0 = dst_y0 * w, i1 = dst_y1 * w;
-        convolve_finish_kernel<<<(unsigned)((i1 - i0 + 255) / 256), 256, 0, s>>>(d_partial, (int)npix, splits, cnt, i0, i1, out_dev + (size_t)first * npix * 3);
+        const int npx = (dst_y1 - dst_y0) * w;
+        convolve_finish_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(d_partial, w, h, (int)npix, cnt, dst_y0, dst_y1, tiles_x, units, (int)ctas,
+                                                                             out_dev + (size_t)first * npix * 3);
         e = cudaGetLastError();
     }
     cudaFreeAsync(d_partial, s);
