@@ -44,6 +44,17 @@ __global__ void wait_flags_kernel(const unsigned int *flags, int n, unsigned int
     }
 }
 
+// CUDA loads kernels lazily, and loading one can need the device to drain — which a spinning wait kernel on the same
+// device (several ranks on one GPU: tests, or a host that drives two contexts) would block until its time-out.
+// rmdf_create loads both kernels up front.
+cudaError_t preload_frame_sync_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, frame_begin_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, wait_flags_kernel);
+    return e;
+}
+
 cudaError_t launch_frame_begin(unsigned int *ctrl, unsigned int seq, cudaStream_t s)
 {
     frame_begin_kernel<<<1, 32, 0, s>>>(ctrl, seq);

@@ -146,6 +146,7 @@ extern "C" int rmdf_create(rmdf_ctx **out, int device)
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * C_NSLOTS);
     if (err == cudaSuccess) err = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS);
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_cornell, sizeof(float4) * kCornellF4);
+    if (err == cudaSuccess) err = preload_frame_sync_kernels();
     if (err != cudaSuccess) {
         fail(RMDF_ERR_CUDA, "rmdf_create: %s", cudaGetErrorString(err));
         rmdf_destroy(ctx);

@@ -77,6 +77,7 @@ cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int f
 cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s);
 cudaError_t measure_fp32_peak(int sm_count, cudaStream_t s, float *tflops, float *sm_mhz);
 cudaError_t measure_mufu_peak(int sm_count, cudaStream_t s, float *gops);
+cudaError_t preload_frame_sync_kernels();
 cudaError_t launch_frame_begin(unsigned int *ctrl, unsigned int seq, cudaStream_t s);
 cudaError_t launch_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int timeout_ms, unsigned int *status, cudaStream_t s);
 cudaError_t launch_mip_resolve(const uint32_t *in_dev, int w, int h, int levels, uint32_t *out_dev, cudaStream_t s);

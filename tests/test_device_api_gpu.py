@@ -184,7 +184,7 @@ def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
                 assert r.frameSyncStatus() == 0
             assert sum(r.counters()["samples"] for r in srs) == w * h          # every sample exactly once
         # Julia through the same protocol
-        jw, jh = 2048, 1024
+        jw, jh = w, h                                         # the same output size: the shared buffer holds n_out words
         wantj = srs[0].juliaAnimated(jw, jh, None, False, 7.0, resolve_log2=k)
         for rank in reversed(range(world)):
             srs[rank].frameBegin(ctrl, rank, world, 4, 5000)
