@@ -33,7 +33,6 @@
 namespace rmdf {
 
 constexpr int CV_DX = 32, CV_DY = 8, CV_THREADS = CV_DX * CV_DY;
-constexpr int CV_SEGS = 3;             // a CTA's unit range touches at most this many destination tiles (see launch_convolve)
 
 // Work decomposition.  The sweep is tiles × h "row units": destination tile t (32×8 pixels) against source row y.
 // The grid is a whole number of CTAs per SM and CTA c owns the contiguous unit range [c·U/C, (c+1)·U/C) of the
@@ -43,13 +42,13 @@ constexpr int CV_SEGS = 3;             // a CTA's unit range touches at most thi
 // in ascending CTA order (deterministic, no float atomics).
 //
 // tab: [dst_w][src_w] cos|φ_L − φ_x| ; cth/sth: cos/sin θ per row (host, libm)
-// partial: [C·CV_SEGS][CV_THREADS][13]  (4 powers × rgb, n)
+// partial: [C·segs][CV_THREADS][13]  (4 powers × rgb, n); segs = the most tiles one range can meet
 template <bool CHAIN>
 __global__ void __launch_bounds__(CV_THREADS)
 convolve_kernel(const float *__restrict__ src, int w, int h, const float *__restrict__ tab,
                 const float *__restrict__ cth, const float *__restrict__ sth,
                 float p0, float p1, float p2, float p3, int np,
-                int dst_y0, int dst_y1, int tiles_x, long long units, float *__restrict__ partial)
+                int dst_y0, int dst_y1, int tiles_x, long long units, int segs, float *__restrict__ partial)
 {
     extern __shared__ float smem[];
     float *s_tab = smem;                                  // [w][CV_DX]  (transposed slice)
@@ -113,8 +112,8 @@ convolve_kernel(const float *__restrict__ src, int w, int h, const float *__rest
                 a23[0] = fma2(px.x, q23, a23[0]); a23[1] = fma2(px.y, q23, a23[1]); a23[2] = fma2(px.z, q23, a23[2]);
             }
         }
-        if (seg < CV_SEGS) {
-            float *o = partial + (((size_t)blockIdx.x * CV_SEGS + seg) * CV_THREADS + threadIdx.x) * 13;
+        if (seg < segs) {
+            float *o = partial + (((size_t)blockIdx.x * segs + seg) * CV_THREADS + threadIdx.x) * 13;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) { o[ch] = a01[ch].x; o[3 + ch] = a01[ch].y; o[6 + ch] = a23[ch].x; o[9 + ch] = a23[ch].y; }
             o[12] = (float)n;
@@ -126,7 +125,7 @@ convolve_kernel(const float *__restrict__ src, int w, int h, const float *__rest
 // out[p][y][x][c] = Σ_segments acc / Σ_segments n   ("divide sum by number of hemisphere samples", :231-232).
 // One thread per destination pixel; its segments are those of the CTAs whose unit range meets the pixel's tile.
 __global__ void convolve_finish_kernel(const float *__restrict__ partial, int w, int h, int npix, int np, int dst_y0, int dst_y1,
-                                       int tiles_x, long long units, int ctas, float *__restrict__ out)
+                                       int tiles_x, long long units, int ctas, int segs, float *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = dst_y1 - dst_y0;
@@ -144,7 +143,7 @@ __global__ void convolve_finish_kernel(const float *__restrict__ partial, int w,
         if (u1 <= lo) continue;
         if (u0 >= hi) break;
         const int seg = tile - (int)(u0 / h);                                      // 0 for the tile the range starts in
-        const float *p = partial + (((size_t)c * CV_SEGS + seg) * CV_THREADS + t) * 13;
+        const float *p = partial + (((size_t)c * segs + seg) * CV_THREADS + t) * 13;
         for (int k = 0; k < 12; k++) acc[k] += p[k];
         n += p[12];
     }
@@ -199,8 +198,8 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
     const int tiles_x = (w + CV_DX - 1) / CV_DX, tiles_y = (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY;
     const long long units = (long long)tiles_x * tiles_y * h;
     const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
-    // a whole number of CTAs per SM (as many as are resident), never so many that a unit range is shorter than h/2 rows
-    // (then a range meets at most CV_SEGS = 3 tiles) nor more than there are units
+    // as many CTAs as are resident at once (a whole number per SM), at most one per unit; a range of L units meets at
+    // most ceil(L / h) + 1 destination tiles
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -208,10 +207,9 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
     cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, convolve_kernel<true>, CV_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     long long ctas = (long long)sms * per_sm;
-    while (ctas > sms && units / ctas < (h + 1) / 2) ctas -= sms;
-    if (units / ctas < (h + 1) / 2) ctas = units / ((h + 1) / 2) > 0 ? units / ((h + 1) / 2) : 1;
     if (ctas > units) ctas = units;
-    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * (size_t)ctas * CV_SEGS * CV_THREADS * 13, s)) != cudaSuccess) return e;
+    const int segs = (int)(((units + ctas - 1) / ctas + h - 1) / h) + 1;
+    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * (size_t)ctas * segs * CV_THREADS * 13, s)) != cudaSuccess) return e;
     for (int first = 0; first < np && e == cudaSuccess; first += 4) {
         const int cnt = (np - first < 4) ? np - first : 4;
         float p[4] = { 0, 0, 0, 0 };
@@ -219,14 +217,14 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
         const bool chain = cnt == 4 && p[0] == 1.0f && p[1] == 8.0f && p[2] == 64.0f && p[3] == 512.0f;
         if (chain)
             convolve_kernel<true><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                          p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, d_partial);
+                                                                          p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, segs, d_partial);
         else
             convolve_kernel<false><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                           p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, d_partial);
+                                                                           p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, segs, d_partial);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
         const int npx = (dst_y1 - dst_y0) * w;
-        convolve_finish_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(d_partial, w, h, (int)npix, cnt, dst_y0, dst_y1, tiles_x, units, (int)ctas,
+        convolve_finish_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(d_partial, w, h, (int)npix, cnt, dst_y0, dst_y1, tiles_x, units, (int)ctas, segs,
                                                                              out_dev + (size_t)first * npix * 3);
         e = cudaGetLastError();
     }
