@@ -34,45 +34,77 @@ namespace rmdf {
 
 constexpr int CV_DX = 32, CV_DY = 8, CV_THREADS = CV_DX * CV_DY;
 
-// Work decomposition.  The sweep is tiles × h "row units": destination tile t (32×8 pixels) against source row y.
-// The grid is a whole number of CTAs per SM and CTA c owns the contiguous unit range [c·U/C, (c+1)·U/C) of the
-// tile-major list — every CTA gets the same amount of work to within one source row (round 1 launched 512 equal
-// CTAs on 148 SMs: 3 or 4 per SM, i.e. 86 % balance).  A range that crosses a tile boundary is processed as two
-// segments; each segment writes one partial sum per destination pixel and the finish kernel adds a pixel's partials
-// in ascending CTA order (deterministic, no float atomics).
+// Work decomposition.  A chunk = destination tile t (32×8 pixels) × CV_ROWS source rows; chunks are ordered
+// tile-major and claimed one at a time from an atomic counter by a persistent grid (as many CTAs as are resident).
+// Round 1 launched 512 equal CTAs on 148 SMs (3 or 4 per SM, 86 % balance); with the skipping below the cost of a
+// chunk also varies by a factor of four, so the deal has to be dynamic.  Every chunk writes one partial sum per
+// destination pixel at its own place in `partial`, and the finish kernel adds a pixel's chunks in ascending source-row
+// order: the result does not depend on which CTA computed what (deterministic, no float atomics).
 //
-// tab: [dst_w][src_w] cos|φ_L − φ_x| ; cth/sth: cos/sin θ per row (host, libm)
-// partial: [C·segs][CV_THREADS][13]  (4 powers × rgb, n); segs = the most tiles one range can meet
+// Skipping.  Half of all (dst, src) pairs have cosAngle <= 0 (the source pixel is behind the lobe) and contribute
+// exactly nothing: weight 0, n unchanged.  A warp is 32 destination pixels of ONE destination row, so for a source
+// row y the terms a = cosθ_L·cosθ_P and b = sinθ_L·sinθ_P are the same for all its lanes, and cosAngle = a + b·tab is
+// monotonic in tab (each rounding is monotonic).  With the largest and smallest table entry of a block of 32 source
+// columns × the tile's 32 destination columns (s_ext, built when the table slice is loaded) the warp knows without a
+// vote — and bit-exactly — whether ANY pair of the block is positive, and skips the block if none is.
+//
+// srcw: the source premultiplied by sinθ_P as float4 (premultiply_kernel), read with one 128-bit load per pixel that
+//       is uniform across the warp (L1-resident: a source row is 4 KB); no staging, no barrier inside a chunk
+// tabT: [tiles_x][src_w][32] cos|φ_L − φ_x|, the table slice of a tile contiguous (coalesced 32 KB per chunk);
+//       cth/sth: cos/sin θ per row (host, libm)
+// partial: [chunks][CV_THREADS][13]  (4 powers × rgb, n)
+constexpr int CV_ROWS = 4;
+
+__global__ void premultiply_kernel(const float *__restrict__ src, int npix, int w, const float *__restrict__ sth, float4 *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float ps = sth[i / w];
+    out[i] = make_float4(src[i * 3] * ps, src[i * 3 + 1] * ps, src[i * 3 + 2] * ps, 0.0f);
+}
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(CV_THREADS)
-convolve_kernel(const float *__restrict__ src, int w, int h, const float *__restrict__ tab,
+convolve_kernel(const float4 *__restrict__ srcw, int w, int h, const float *__restrict__ tabT,
                 const float *__restrict__ cth, const float *__restrict__ sth,
                 float p0, float p1, float p2, float p3, int np,
-                int dst_y0, int dst_y1, int tiles_x, long long units, int segs, float *__restrict__ partial)
+                int dst_y0, int dst_y1, int tiles_x, int chunks_per_tile, int n_chunks,
+                unsigned int *__restrict__ queue, float *__restrict__ partial)
 {
     extern __shared__ float smem[];
-    float *s_tab = smem;                                  // [w][CV_DX]  (transposed slice)
-    float4 *s_row = reinterpret_cast<float4 *>(smem + (size_t)w * CV_DX);   // [2][w]
+    float *s_tab = smem;                                  // [w][CV_DX]  (the tile's table slice)
+    float *s_ext = smem + (size_t)w * CV_DX;              // [2][ceil(w/32)]  max / min of the slice per block of 32 source columns
+    __shared__ int s_chunk;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    long long u = (long long)blockIdx.x * units / gridDim.x;
-    const long long u1 = (long long)(blockIdx.x + 1) * units / gridDim.x;
+    const int groups = (w + 31) >> 5;
     int loaded_tx = -1;
 
-    for (int seg = 0; u < u1; seg++) {
-        const int tile = (int)(u / h), y_begin = (int)(u - (long long)tile * h);
-        const int y_end = (int)min((long long)h, y_begin + (u1 - u));
+    for (;;) {
+        __syncthreads();                                   // everybody is done with s_chunk and s_tab of the previous chunk
+        if (threadIdx.x == 0) s_chunk = (int)atomicAdd(queue, 1u);
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int tile = chunk / chunks_per_tile, y_begin = (chunk - tile * chunks_per_tile) * CV_ROWS;
+        const int y_end = min(h, y_begin + CV_ROWS);
         const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-        const int dstx = tile_x * CV_DX + tx, dsty = dst_y0 + tile_y * CV_DY + ty;       // destination rows [dst_y0, dst_y1)
-        const bool valid = dstx < w && dsty < dst_y1;
-        __syncthreads();                                   // the previous segment is done with s_tab / s_row
         if (tile_x != loaded_tx) {
-            for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) {
-                const int sx = i / CV_DX, dx = tile_x * CV_DX + (i % CV_DX);
-                s_tab[i] = (dx < w) ? tab[(size_t)dx * w + sx] : 0.0f;
+            const float *slice = tabT + (size_t)tile_x * w * CV_DX;
+            for (int i = threadIdx.x; i < w * CV_DX; i += CV_THREADS) s_tab[i] = slice[i];
+            __syncthreads();
+            for (int g = ty; g < groups; g += CV_DY) {     // one warp per block of 32 source columns
+                float mx = -2.0f, mn = 2.0f;
+                for (int sx = g * 32; sx < min(w, g * 32 + 32); sx++) { const float t = s_tab[sx * CV_DX + tx]; mx = fmaxf(mx, t); mn = fminf(mn, t); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+                if (tx == 0) { s_ext[g] = mx; s_ext[groups + g] = mn; }
             }
+            __syncthreads();
             loaded_tx = tile_x;
         }
-        const float lobe_cos = valid ? cth[dsty] : 0.0f, lobe_sin = valid ? sth[dsty] : 0.0f;
+        // a destination row beyond dst_y1 behaves like the last valid one (warp-uniform either way), its sums are discarded
+        const int dsty = min(dst_y0 + tile_y * CV_DY + ty, dst_y1 - 1);
+        const float lobe_cos = cth[dsty], lobe_sin = sth[dsty];
         // accumulators: powers (1, 8) and (64, 512) side by side in 64-bit register pairs — one FFMA2 per channel and
         // pair does two individually rounded FMAs in one issue slot (csrc/packed_f32.cuh); generic powers use .x/.y too
         f2 a01[3], a23[3];
@@ -81,51 +113,48 @@ convolve_kernel(const float *__restrict__ src, int w, int h, const float *__rest
         int n = 0;
 
         for (int y = y_begin; y < y_end; y++) {
-            float4 *row = s_row + (size_t)((y - y_begin) & 1) * w;
-            const float ps = sth[y];
-            for (int i = threadIdx.x; i < w; i += CV_THREADS) {
-                const float *sp = src + ((size_t)y * w + i) * 3;
-                row[i] = make_float4(sp[0] * ps, sp[1] * ps, sp[2] * ps, 0.0f);
-            }
-            __syncthreads();                               // double-buffered: one barrier per row
-            const float a = __fmul_rn(lobe_cos, cth[y]);   // thetaLobeCos * thetaPxCos
-            const float b = __fmul_rn(lobe_sin, ps);       // thetaLobeSin * thetaPxSin
+            const float a = __fmul_rn(lobe_cos, cth[y]);   // thetaLobeCos * thetaPxCos      (uniform across the warp)
+            const float b = __fmul_rn(lobe_sin, sth[y]);   // thetaLobeSin * thetaPxSin
+            const float4 *row = srcw + (size_t)y * w;
+            for (int g = 0; g < groups; g++) {
+                // the block's largest cosAngle: a + b·(largest table entry if b >= 0, else the smallest)
+                const float t_ext = (b >= 0.0f) ? s_ext[g] : s_ext[groups + g];
+                if (!(__fadd_rn(a, __fmul_rn(b, t_ext)) > 0.0f)) continue;
+                const int x_end = min(w, g * 32 + 32);
 #pragma unroll 4
-            for (int x = 0; x < w; x++) {
-                // cosAngle, HDREnvMap.hs:242-244, same rounding sequence as the reference
-                const float c = __fadd_rn(a, __fmul_rn(b, s_tab[x * CV_DX + tx]));
-                const float4 px = row[x];
-                const bool pos = c > 0.0f;
-                const float cc = fmaxf(c, 0.0f);
-                n += pos ? 1 : 0;
-                f2 q01, q23;
-                if (CHAIN) {                               // powers 1, 8, 64, 512 from nine squarings
-                    const float c2 = cc * cc, c4 = c2 * c2, c8 = c4 * c4;
-                    const float c16 = c8 * c8, c32 = c16 * c16, c64 = c32 * c32;
-                    const float c128 = c64 * c64, c256 = c128 * c128, c512 = c256 * c256;
-                    q01 = F2(cc, c8); q23 = F2(c64, c512);
-                } else {
-                    q01 = F2(pos ? powf(c, p0) : 0.0f, (np > 1 && pos) ? powf(c, p1) : 0.0f);
-                    q23 = F2((np > 2 && pos) ? powf(c, p2) : 0.0f, (np > 3 && pos) ? powf(c, p3) : 0.0f);
+                for (int x = g * 32; x < x_end; x++) {
+                    // cosAngle, HDREnvMap.hs:242-244, same rounding sequence as the reference
+                    const float c = __fadd_rn(a, __fmul_rn(b, s_tab[x * CV_DX + tx]));
+                    const float4 px = __ldg(row + x);
+                    const bool pos = c > 0.0f;
+                    const float cc = fmaxf(c, 0.0f);
+                    n += pos ? 1 : 0;
+                    f2 q01, q23;
+                    if (CHAIN) {                           // powers 1, 8, 64, 512 from nine squarings
+                        const float c2 = cc * cc, c4 = c2 * c2, c8 = c4 * c4;
+                        const float c16 = c8 * c8, c32 = c16 * c16, c64 = c32 * c32;
+                        const float c128 = c64 * c64, c256 = c128 * c128, c512 = c256 * c256;
+                        q01 = F2(cc, c8); q23 = F2(c64, c512);
+                    } else {
+                        q01 = F2(pos ? powf(c, p0) : 0.0f, (np > 1 && pos) ? powf(c, p1) : 0.0f);
+                        q23 = F2((np > 2 && pos) ? powf(c, p2) : 0.0f, (np > 3 && pos) ? powf(c, p3) : 0.0f);
+                    }
+                    a01[0] = fma2(px.x, q01, a01[0]); a01[1] = fma2(px.y, q01, a01[1]); a01[2] = fma2(px.z, q01, a01[2]);
+                    a23[0] = fma2(px.x, q23, a23[0]); a23[1] = fma2(px.y, q23, a23[1]); a23[2] = fma2(px.z, q23, a23[2]);
                 }
-                a01[0] = fma2(px.x, q01, a01[0]); a01[1] = fma2(px.y, q01, a01[1]); a01[2] = fma2(px.z, q01, a01[2]);
-                a23[0] = fma2(px.x, q23, a23[0]); a23[1] = fma2(px.y, q23, a23[1]); a23[2] = fma2(px.z, q23, a23[2]);
             }
         }
-        if (seg < segs) {
-            float *o = partial + (((size_t)blockIdx.x * segs + seg) * CV_THREADS + threadIdx.x) * 13;
+        float *o = partial + ((size_t)chunk * CV_THREADS + threadIdx.x) * 13;
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) { o[ch] = a01[ch].x; o[3 + ch] = a01[ch].y; o[6 + ch] = a23[ch].x; o[9 + ch] = a23[ch].y; }
-            o[12] = (float)n;
-        }
-        u += y_end - y_begin;
+        for (int ch = 0; ch < 3; ch++) { o[ch] = a01[ch].x; o[3 + ch] = a01[ch].y; o[6 + ch] = a23[ch].x; o[9 + ch] = a23[ch].y; }
+        o[12] = (float)n;
     }
 }
 
-// out[p][y][x][c] = Σ_segments acc / Σ_segments n   ("divide sum by number of hemisphere samples", :231-232).
-// One thread per destination pixel; its segments are those of the CTAs whose unit range meets the pixel's tile.
-__global__ void convolve_finish_kernel(const float *__restrict__ partial, int w, int h, int npix, int np, int dst_y0, int dst_y1,
-                                       int tiles_x, long long units, int ctas, int segs, float *__restrict__ out)
+// out[p][y][x][c] = Σ_chunks acc / Σ_chunks n   ("divide sum by number of hemisphere samples", :231-232).
+// One thread per destination pixel, its tile's chunks in ascending source-row order.
+__global__ void convolve_finish_kernel(const float *__restrict__ partial, int w, int npix, int np, int dst_y0, int dst_y1,
+                                       int tiles_x, int chunks_per_tile, float *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = dst_y1 - dst_y0;
@@ -133,17 +162,10 @@ __global__ void convolve_finish_kernel(const float *__restrict__ partial, int w,
     const int dsty = dst_y0 + i / w, dstx = i % w;
     const int tile = ((dsty - dst_y0) / CV_DY) * tiles_x + dstx / CV_DX;
     const int t = ((dsty - dst_y0) % CV_DY) * CV_DX + (dstx % CV_DX);              // thread index inside the tile's CTA
-    const long long lo = (long long)tile * h, hi = lo + h;                         // the tile's units
     float acc[12], n = 0.0f;
     for (int k = 0; k < 12; k++) acc[k] = 0.0f;
-    int c = (int)(lo * ctas / units);                                              // a CTA at or just before the first owner
-    while (c > 0 && (long long)c * units / ctas > lo) c--;
-    for (; c < ctas; c++) {
-        const long long u0 = (long long)c * units / ctas, u1 = (long long)(c + 1) * units / ctas;
-        if (u1 <= lo) continue;
-        if (u0 >= hi) break;
-        const int seg = tile - (int)(u0 / h);                                      // 0 for the tile the range starts in
-        const float *p = partial + (((size_t)c * segs + seg) * CV_THREADS + t) * 13;
+    for (int c = 0; c < chunks_per_tile; c++) {
+        const float *p = partial + (((size_t)tile * chunks_per_tile + c) * CV_THREADS + t) * 13;
         for (int k = 0; k < 12; k++) acc[k] += p[k];
         n += p[12];
     }
@@ -152,8 +174,10 @@ __global__ void convolve_finish_kernel(const float *__restrict__ partial, int w,
         for (int ch = 0; ch < 3; ch++) out[((size_t)p * npix + pix) * 3 + ch] = acc[p * 3 + ch] / n;
 }
 
-// Host-side tables, same libm calls and rounding as HDREnvMap.hs:223-236.
-static void convolve_tables(int w, int h, float *tab, float *cth, float *sth)
+// Host-side tables, same libm calls and rounding as HDREnvMap.hs:223-236.  The φ table is stored per destination tile
+// column block: tabT[tile_x][sx][j] = cos|φ_L(tile_x·32 + j) − φ_x(sx)|; destination columns beyond the image repeat
+// the last one (their lanes compute and discard; the per-block extrema stay those of real columns).
+static void convolve_tables(int w, int h, float *tabT, float *cth, float *sth)
 {
     const float pi = 3.14159265358979323846f;
     for (int y = 0; y < h; y++) {
@@ -161,18 +185,22 @@ static void convolve_tables(int w, int h, float *tab, float *cth, float *sth)
         cth[y] = cosf(theta);
         sth[y] = sinf(theta);
     }
-    for (int dx = 0; dx < w; dx++) {
-        const float phi_lobe = (float)dx / (float)(w - 1) * 2.0f * pi;
-        for (int sx = 0; sx < w; sx++)
-            tab[(size_t)dx * w + sx] = cosf(fabsf(phi_lobe - (float)sx / (float)(w - 1) * 2.0f * pi));
-    }
+    const int tiles_x = (w + CV_DX - 1) / CV_DX;
+    for (int t = 0; t < tiles_x; t++)
+        for (int j = 0; j < CV_DX; j++) {
+            const int dx = (t * CV_DX + j < w) ? t * CV_DX + j : w - 1;
+            const float phi_lobe = (float)dx / (float)(w - 1) * 2.0f * pi;
+            for (int sx = 0; sx < w; sx++)
+                tabT[((size_t)t * w + sx) * CV_DX + j] = cosf(fabsf(phi_lobe - (float)sx / (float)(w - 1) * 2.0f * pi));
+        }
 }
 
 cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *powers_host, int np,
                             float *out_dev, int dst_y0, int dst_y1, cudaStream_t s)
 {
     cudaError_t e;
-    const size_t ntab = (size_t)w * w;
+    const int tiles_x = (w + CV_DX - 1) / CV_DX, tiles_y = (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY;
+    const size_t ntab = (size_t)tiles_x * w * CV_DX;
     const size_t nall = ntab + 2 * (size_t)h;
     // The tables depend on (w, h) only — w² + 2h libm calls and a 260 KB upload — so the device copy is kept per
     // (device, w, h) for the next sweep of the same size (a few sizes at most: never freed before exit).
@@ -193,42 +221,51 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
             cache.push_back({ dev, w, h, d_tab });
         }
     }
-    float *d_partial = nullptr;
     const size_t npix = (size_t)w * h;
-    const int tiles_x = (w + CV_DX - 1) / CV_DX, tiles_y = (dst_y1 - dst_y0 + CV_DY - 1) / CV_DY;
-    const long long units = (long long)tiles_x * tiles_y * h;
-    const size_t smem = sizeof(float) * (size_t)w * CV_DX + sizeof(float4) * 2 * (size_t)w;
-    // as many CTAs as are resident at once (a whole number per SM), at most one per unit; a range of L units meets at
-    // most ceil(L / h) + 1 destination tiles
+    const int chunks_per_tile = (h + CV_ROWS - 1) / CV_ROWS;
+    const int n_chunks = tiles_x * tiles_y * chunks_per_tile;
+    const size_t smem = sizeof(float) * ((size_t)w * CV_DX + 2 * (size_t)((w + 31) / 32));
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(convolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(convolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, convolve_kernel<true>, CV_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    long long ctas = (long long)sms * per_sm;
-    if (ctas > units) ctas = units;
-    const int segs = (int)(((units + ctas - 1) / ctas + h - 1) / h) + 1;
-    if ((e = cudaMallocAsync(&d_partial, sizeof(float) * (size_t)ctas * segs * CV_THREADS * 13, s)) != cudaSuccess) return e;
+    int ctas = sms * per_sm;                               // persistent: every CTA is resident and pulls chunks
+    if (ctas > n_chunks) ctas = n_chunks;
+    // scratch: [64 B queue counters, one per batch of four powers][partial sums][premultiplied source]
+    const int batches = (np + 3) / 4;
+    const size_t q_bytes = ((size_t)batches * sizeof(unsigned int) + 255) & ~(size_t)255;
+    const size_t p_bytes = sizeof(float) * (size_t)n_chunks * CV_THREADS * 13;
+    unsigned char *d_scratch = nullptr;
+    if ((e = cudaMallocAsync(&d_scratch, q_bytes + p_bytes + sizeof(float4) * npix, s)) != cudaSuccess) return e;
+    unsigned int *d_queue = reinterpret_cast<unsigned int *>(d_scratch);
+    float *d_partial = reinterpret_cast<float *>(d_scratch + q_bytes);
+    float4 *d_srcw = reinterpret_cast<float4 *>(d_scratch + q_bytes + p_bytes);
+    e = cudaMemsetAsync(d_queue, 0, q_bytes, s);
+    if (e == cudaSuccess) {
+        premultiply_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(src_dev, (int)npix, w, d_tab + ntab + h, d_srcw);
+        e = cudaGetLastError();
+    }
     for (int first = 0; first < np && e == cudaSuccess; first += 4) {
         const int cnt = (np - first < 4) ? np - first : 4;
         float p[4] = { 0, 0, 0, 0 };
         for (int k = 0; k < cnt; k++) p[k] = powers_host[first + k];
         const bool chain = cnt == 4 && p[0] == 1.0f && p[1] == 8.0f && p[2] == 64.0f && p[3] == 512.0f;
         if (chain)
-            convolve_kernel<true><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                          p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, segs, d_partial);
+            convolve_kernel<true><<<(unsigned)ctas, CV_THREADS, smem, s>>>(d_srcw, w, h, d_tab, d_tab + ntab, d_tab + ntab + h, p[0], p[1], p[2], p[3], cnt,
+                                                                          dst_y0, dst_y1, tiles_x, chunks_per_tile, n_chunks, d_queue + first / 4, d_partial);
         else
-            convolve_kernel<false><<<(unsigned)ctas, CV_THREADS, smem, s>>>(src_dev, w, h, d_tab, d_tab + ntab, d_tab + ntab + h,
-                                                                           p[0], p[1], p[2], p[3], cnt, dst_y0, dst_y1, tiles_x, units, segs, d_partial);
+            convolve_kernel<false><<<(unsigned)ctas, CV_THREADS, smem, s>>>(d_srcw, w, h, d_tab, d_tab + ntab, d_tab + ntab + h, p[0], p[1], p[2], p[3], cnt,
+                                                                           dst_y0, dst_y1, tiles_x, chunks_per_tile, n_chunks, d_queue + first / 4, d_partial);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
         const int npx = (dst_y1 - dst_y0) * w;
-        convolve_finish_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(d_partial, w, h, (int)npix, cnt, dst_y0, dst_y1, tiles_x, units, (int)ctas, segs,
+        convolve_finish_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(d_partial, w, (int)npix, cnt, dst_y0, dst_y1, tiles_x, chunks_per_tile,
                                                                              out_dev + (size_t)first * npix * 3);
         e = cudaGetLastError();
     }
-    cudaFreeAsync(d_partial, s);
+    cudaFreeAsync(d_scratch, s);
     return e;
 }
 

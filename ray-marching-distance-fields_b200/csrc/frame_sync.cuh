@@ -24,10 +24,12 @@ struct FrameSync {
     unsigned int *signal;              // arrival flag to publish when the last CTA has stored; nullptr = none
     unsigned int  signal_value;
     int           queue_sys;           // the queue is shared with other GPUs: claim with a system-scope atomic
-    int           prefetch;            // claim the next item before working on the current one (hides a NVLink round
-                                       // trip; only with many items per warp — an item claimed early is an item that
-                                       // an idle warp can no longer take, which lengthens the tail of a small frame:
-                                       // BASELINE config 1 went 0.099 → 0.124 ms with unconditional prefetching)
+    unsigned int  prefetch_margin;     // 0: claim an item when the previous one is done.  m > 0: while item + m < n_items
+                                       // the NEXT item is claimed before working on the current one, which hides the
+                                       // NVLink round trip of a shared queue; over the last m items the warps go back to
+                                       // claiming late, so the end of the frame is still dealt dynamically (an item
+                                       // claimed early is an item an idle warp can no longer take: unconditional
+                                       // prefetching cost BASELINE config 1 0.099 → 0.124 ms and 1.4 % at N = 2)
 };
 
 // lane 0 claims; the value is broadcast by the caller when it needs it, so the atomic's latency (a NVLink round trip

@@ -110,14 +110,15 @@ julia_kernel(const JuliaParams P)
     const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
-    const bool prefetch = P.sync.prefetch != 0;
     unsigned claimed = 0;
-    if (prefetch && lane == 0) claimed = claim_item(P.sync);
+    bool have = false;                                            // warp-uniform: `claimed` already holds the next item
     for (;;) {
-        if (!prefetch && lane == 0) claimed = claim_item(P.sync);
+        // ---- one work item (see FrameSync::prefetch_margin for when the next one is claimed early) ----
+        if (!have && lane == 0) claimed = claim_item(P.sync);
         const unsigned item = __shfl_sync(0xffffffffu, claimed, 0);
         if (item >= (unsigned)P.n_items) break;
-        if (prefetch && lane == 0) claimed = claim_item(P.sync);  // the next item: its latency overlaps this one
+        have = P.sync.prefetch_margin != 0u && item + P.sync.prefetch_margin < (unsigned)P.n_items;
+        if (have && lane == 0) claimed = claim_item(P.sync);
         // item → (band of this rank, block row inside the band, block column)
         const int per_band = P.blocks_x * P.blocks_y;
         const int band_k = (int)item / per_band, in_band = (int)item - band_k * per_band;

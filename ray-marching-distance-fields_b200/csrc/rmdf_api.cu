@@ -147,6 +147,16 @@ extern "C" int rmdf_create(rmdf_ctx **out, int device)
     if (err == cudaSuccess) err = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * C_NSLOTS);
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_cornell, sizeof(float4) * kCornellF4);
     if (err == cudaSuccess) err = preload_frame_sync_kernels();
+    if (err == cudaSuccess) {
+        // stream-ordered scratch (the convolution's partial sums) stays in the device's pool between calls instead of
+        // going back to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (err != cudaSuccess) {
         fail(RMDF_ERR_CUDA, "rmdf_create: %s", cudaGetErrorString(err));
         rmdf_destroy(ctx);
@@ -248,7 +258,7 @@ extern "C" int rmdf_envmap_convolve_rows_device(rmdf_ctx *ctx, const void *rgb_d
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_convolve: %s", cudaGetErrorString(e));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches += 2 * (uint64_t)((np + 3) / 4);
+    ctx->launches += 1 + 2 * (uint64_t)((np + 3) / 4);          // premultiply + (convolve, finish) per batch of four powers
     return RMDF_OK;
 }
 extern "C" int rmdf_envmap_convolve_device(rmdf_ctx *ctx, const void *rgb_dev, int w, int h,
@@ -714,7 +724,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.cornell = ctx->d_cornell;
     mp.out = fb_dev;
     mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
-    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.prefetch = 0;
+    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.prefetch_margin = 0;
     int world = 1;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
         if (wl.rect_mode != 0 || p->layout != RMDF_LAYOUT_FRAME)
@@ -760,7 +770,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
     mp.n_items = (int)n_items;
     if (mp.n_items == 0) return RMDF_OK;
-    mp.sync.prefetch = (mp.sync.queue_sys && n_items >= (int64_t)resident_warps * 16) ? 1 : 0;
+    mp.sync.prefetch_margin = mp.sync.queue_sys ? 2u * (unsigned)resident_warps : 0u;
     int grid = ctas_per_sm * ctx->sm_count;
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
@@ -857,7 +867,7 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->n_items = (int)n;
     jp->out_stride = w >> k;
     jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
-    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.prefetch = 0;
+    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.prefetch_margin = 0;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
 }
@@ -873,7 +883,7 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
         }
         jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1;
         jp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; jp.sync.signal_value = ctx->sync_seq;
-        jp.sync.prefetch = (jp.n_items >= (int64_t)julia_ctas_per_sm() * ctx->sm_count * kWarpsPerCta * ctx->sync_world * 16) ? 1 : 0;
+        jp.sync.prefetch_margin = 2u * (unsigned)(julia_ctas_per_sm() * ctx->sm_count * kWarpsPerCta * ctx->sync_world);
         ctx->sync_ctrl = nullptr;
     }
     int grid = julia_ctas_per_sm() * ctx->sm_count;
