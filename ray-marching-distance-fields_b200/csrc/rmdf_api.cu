@@ -54,7 +54,7 @@ struct rmdf_ctx {
     unsigned int *d_queue = nullptr;   // [0] work queue, [1] CTA-exit counter of the running kernel, [2] wait status
     // multi-GPU frame assembly (rmdf_frame_begin): applies to the next render / Julia launch, then clears
     unsigned int *sync_ctrl = nullptr;
-    int sync_rank = 0, sync_world = 1;
+    int sync_rank = 0, sync_world = 1, sync_timeout_ms = 0;
     unsigned int sync_seq = 0;
     unsigned long long *d_counters = nullptr;
     uint64_t launches = 0;
@@ -775,6 +775,12 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
 
+    if (mp.sync.queue_sys && ctx->sync_rank != 0) {        // rank != 0 of a multi-GPU frame: wait for rank 0's "go" (see rmdf_frame_begin)
+        cudaError_t ew = launch_wait_flags(mp.sync.queue - kSyncQueueWord + kSyncGoWord, 1, mp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
+                                           ctx->d_queue + 2, ctx->stream);
+        if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
+        ctx->launches++;
+    }
     CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = (p->mode == RMDF_MODE_FAST) ? launch_march_fast(mp, grid, ctx->stream)
@@ -889,6 +895,12 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
     int grid = julia_ctas_per_sm() * ctx->sm_count;
     const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
+    if (jp.sync.queue_sys && ctx->sync_rank != 0) {        // rank != 0 of a multi-GPU frame: wait for rank 0's "go"
+        cudaError_t ew = launch_wait_flags(jp.sync.queue - kSyncQueueWord + kSyncGoWord, 1, jp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
+                                           ctx->d_queue + 2, ctx->stream);
+        if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
+        ctx->launches++;
+    }
     CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_julia(jp, grid, ctx->stream);
@@ -1033,12 +1045,15 @@ extern "C" int rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int wor
     if (timeout_ms <= 0) timeout_ms = 10000;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     unsigned int *ctrl = (unsigned int *)ctrl_dev;
-    cudaError_t e;
-    if (rank == 0) e = launch_frame_begin(ctrl, seq, ctx->stream);                       // queue = 0, then go = seq
-    else           e = launch_wait_flags(ctrl + kSyncGoWord, 1, seq, (unsigned)timeout_ms, ctx->d_queue + 2, ctx->stream);
-    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_frame_begin: %s", cudaGetErrorString(e));
-    ctx->launches++;
-    ctx->sync_ctrl = ctrl; ctx->sync_rank = rank; ctx->sync_world = world; ctx->sync_seq = seq;
+    if (rank == 0) {                                       // queue = 0, then go = seq
+        cudaError_t e = launch_frame_begin(ctrl, seq, ctx->stream);
+        if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_frame_begin: %s", cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    // The other ranks wait for "go" on their stream — but that wait kernel is enqueued by the render call itself, after
+    // it has made sure its own kernel is loaded: CUDA loads kernels lazily and a first load can need the device to
+    // drain, which a spinning wait kernel would hold up until its time-out.
+    ctx->sync_ctrl = ctrl; ctx->sync_rank = rank; ctx->sync_world = world; ctx->sync_seq = seq; ctx->sync_timeout_ms = timeout_ms;
     return RMDF_OK;
 }
 extern "C" int rmdf_frame_end(rmdf_ctx *ctx, void *ctrl_dev, int world, uint32_t seq, int timeout_ms)
