@@ -110,15 +110,11 @@ julia_kernel(const JuliaParams P)
     const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
-    unsigned claimed = 0;
-    bool have = false;                                            // warp-uniform: `claimed` already holds the next item
+    ItemBatch batch;
     for (;;) {
-        // ---- one work item (see FrameSync::prefetch_margin for when the next one is claimed early) ----
-        if (!have && lane == 0) claimed = claim_item(P.sync);
-        const unsigned item = __shfl_sync(0xffffffffu, claimed, 0);
+        // ---- one work item (frame_sync.cuh: claimed singly from a local queue, in guided batches from a shared one) ----
+        const unsigned item = next_item(P.sync, batch, (unsigned)P.n_items, lane);
         if (item >= (unsigned)P.n_items) break;
-        have = P.sync.prefetch_margin != 0u && item + P.sync.prefetch_margin < (unsigned)P.n_items;
-        if (have && lane == 0) claimed = claim_item(P.sync);
         // item → (band of this rank, block row inside the band, block column)
         const int per_band = P.blocks_x * P.blocks_y;
         const int band_k = (int)item / per_band, in_band = (int)item - band_k * per_band;

@@ -724,7 +724,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.cornell = ctx->d_cornell;
     mp.out = fb_dev;
     mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
-    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.prefetch_margin = 0;
+    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.batch_max = 1; mp.sync.batch_div = 1;
     int world = 1;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
         if (wl.rect_mode != 0 || p->layout != RMDF_LAYOUT_FRAME)
@@ -770,7 +770,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
     mp.n_items = (int)n_items;
     if (mp.n_items == 0) return RMDF_OK;
-    mp.sync.prefetch_margin = mp.sync.queue_sys ? 2u * (unsigned)resident_warps : 0u;
+    if (mp.sync.queue_sys) { mp.sync.batch_max = 8u; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
     int grid = ctas_per_sm * ctx->sm_count;
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
@@ -873,7 +873,7 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->n_items = (int)n;
     jp->out_stride = w >> k;
     jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
-    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.prefetch_margin = 0;
+    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.batch_max = 1; jp->sync.batch_div = 1;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
 }
@@ -889,7 +889,7 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
         }
         jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1;
         jp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; jp.sync.signal_value = ctx->sync_seq;
-        jp.sync.prefetch_margin = 2u * (unsigned)(julia_ctas_per_sm() * ctx->sm_count * kWarpsPerCta * ctx->sync_world);
+        jp.sync.batch_max = 16u; jp.sync.batch_div = 4u * (unsigned)(julia_ctas_per_sm() * ctx->sm_count * kWarpsPerCta * ctx->sync_world);
         ctx->sync_ctrl = nullptr;
     }
     int grid = julia_ctas_per_sm() * ctx->sm_count;
