@@ -305,14 +305,16 @@ def run_ours(args):
     full = dict(resolve_log2=SPP_LOG2, mode=mode)
     grid, skew = par.balanced_grid(FB_W, FB_H, SPP_LOG2, world) if sharded else ((0, 0), 0)
     # N > 1, three ways to assemble the frame on rank 0 (--gather):
-    #   peer (default)  ONE frame-wide work queue in rank 0's memory that all GPUs claim from with system-scope atomics over
-    #                   NVLink (dynamic deal), pixel stores straight into rank 0's frame buffer, arrival flags instead of a
-    #                   barrier (parallel.SharedFrame.begin/end, csrc/frame_sync.cuh)
-    #   peer-static     round 1's path: tiles dealt statically, stores into rank 0's frame buffer, one NCCL barrier
+    #   peer (default)  every rank launches the same frame-wide work list; work item i (a 32x8-sample block) belongs to rank
+    #                   i mod N and goes through the rank's own queue; pixel stores straight into rank 0's frame buffer over
+    #                   NVLink; arrival flags in peer memory instead of a barrier (parallel.SharedFrame.begin/end,
+    #                   csrc/frame_sync.cuh)
+    #   peer-queue      the same, but all GPUs claim items from ONE queue word in rank 0's memory with system-scope atomics
+    #   peer-static     round 1's path: 64x64-sample tiles dealt statically, stores into rank 0's frame buffer, one NCCL barrier
     #   nccl            packed tiles + ONE dist.gather + re-assembly on rank 0
     gather = args.gather if sharded else "none"
     shared = None
-    if gather in ("peer", "peer-static"):
+    if gather in ("peer", "peer-queue", "peer-static"):
         okf = 1
         try:
             shared = par.SharedFrame(sr, OUT_W * OUT_H, world, rank)
@@ -325,7 +327,9 @@ def run_ours(args):
             if shared is not None:
                 shared.close()
             shared, gather = None, "nccl"
-    if gather == "peer" or not sharded:
+    flags_mode = gather in ("peer", "peer-queue")
+    deal = 1 if gather == "peer-queue" else 0
+    if flags_mode or not sharded:
         p = sr.makeParams(scene, None, FB_W, FB_H, TIME, **full)                          # the same full-frame work list on every rank
     elif gather == "peer-static":
         p = sr.makeParams(scene, None, FB_W, FB_H, TIME, shard_rank=rank, shard_count=world, layout=R.LAYOUT_FRAME, shard_grid=grid, shard_skew=skew, **full)
@@ -358,9 +362,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def render_shared(target_ptr):
-        if gather == "peer":
-            shared.begin()                                              # rank 0: queue reset + go; others: wait for go (on the stream)
-            sr.renderDevice(p, target_ptr)                              # claims from the shared queue, signals its arrival flag
+        if flags_mode:
+            shared.begin(deal=deal)                                     # rank 0: queue reset + go; the others wait for go on their stream
+            sr.renderDevice(p, target_ptr)                              # renders this rank's items, publishes its arrival flag
             shared.end()                                                # rank 0's stream waits for every rank's flag
         else:
             sr.renderDevice(p, target_ptr)
@@ -431,11 +435,11 @@ def run_ours(args):
 
     # BASELINE configs[4] at N > 1: the Julia frame through the same shared queue / peer stores / arrival flags
     julia_n = None
-    if sharded and shared is not None and gather == "peer" and not args.no_configs:
+    if sharded and shared is not None and flags_mode and not args.no_configs:
         shared_j = par.SharedFrame(sr, J_OUT_W * J_OUT_H, world, rank)
 
         def step_julia():
-            shared_j.begin()
+            shared_j.begin(deal=deal)
             sr.juliaDevice(J_FB_W, J_FB_H, False, J_TICK, (0, J_FB_H), J_SPP_LOG2, shared_j.ptr)
             shared_j.end()
         ms_j = timed(step_julia, args.steps, 3, events=True)
@@ -495,7 +499,8 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": headline_config(mode_name, {"none": "single GPU",
-                                                  "peer": "one frame-wide work queue in rank 0's memory, claimed by all %d GPUs with system-scope atomics over NVLink (dynamic deal); pixel stores into rank 0's frame buffer; arrival flags, no barrier" % world,
+                                                  "peer": "one frame-wide work list, item i (32x8 samples) -> rank i mod %d through the rank's own queue; pixel stores into rank 0's frame buffer over NVLink; arrival flags in peer memory, no barrier, no NCCL on the data path" % world,
+                                                  "peer-queue": "one frame-wide work queue in rank 0's memory, claimed by all %d GPUs with system-scope atomics over NVLink (dynamic deal); pixel stores into rank 0's frame buffer; arrival flags, no barrier" % world,
                                                   "peer-static": "tiles %dx%d, rank = (tx + %d*ty) mod %d, stores into rank 0's frame buffer over NVLink + one NCCL barrier" % (grid[0], grid[1], skew, world),
                                                   "nccl": "tiles %dx%d, rank = (tx + %d*ty) mod %d, one NCCL gather + re-assembly" % (grid[0], grid[1], skew, world)}[gather],
                                       "flushed between steps (256 MiB write); env maps (2.8 MB) are meant to be L2-resident"),
@@ -603,7 +608,7 @@ def run_julia(args):
     band_h = par.julia_band_height(J_FB_H, J_SPP_LOG2, world)
     n_out = J_OUT_W * J_OUT_H // world
     shared = None
-    if world > 1 and args.gather in ("peer", "peer-static"):     # fused gather, as for the Mandelbulb frame
+    if world > 1 and args.gather in ("peer", "peer-queue", "peer-static"):     # fused gather, as for the Mandelbulb frame
         okf = 1
         try:
             shared = par.SharedFrame(sr, J_OUT_W * J_OUT_H, world, rank)
@@ -624,8 +629,8 @@ def run_julia(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        if shared is not None and args.gather == "peer":                # one frame-wide queue for all GPUs (parallel.SharedFrame)
-            shared.begin()
+        if shared is not None and args.gather in ("peer", "peer-queue"):     # one frame-wide item list for all GPUs (parallel.SharedFrame)
+            shared.begin(deal=1 if args.gather == "peer-queue" else 0)
             sr.juliaDevice(J_FB_W, J_FB_H, False, J_TICK, (0, J_FB_H), J_SPP_LOG2, shared.ptr)
             shared.end()
             return shared_frame
@@ -678,7 +683,7 @@ def run_julia(args):
         line = {"metric": "julia_8k_samples_per_s", "value": samples / (ms_res * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": J_WORKLOAD, "fb": [J_FB_W, J_FB_H], "out": [J_OUT_W, J_OUT_H], "spp": 64,
-                                                "parallelism": ("one frame-wide work queue in rank 0's memory claimed by all %d GPUs over NVLink, stores into rank 0's frame, arrival flags" % world if (shared is not None and args.gather == "peer") else
+                                                "parallelism": ("one frame-wide item list, item i -> rank i mod %d (peer-queue: one shared queue), stores into rank 0's frame over NVLink, arrival flags" % world if (shared is not None and args.gather in ("peer", "peer-queue")) else
                                                                 "row bands of %d rows, band b -> rank b mod %d, %s" % (band_h, world, "stores fused into the kernel over NVLink peer memory + barrier" if shared is not None else "one NCCL gather")) if world > 1 else "single GPU",
                                                 "l2": "flushed between steps (256 MiB write)"},
                 "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 64,
@@ -709,8 +714,9 @@ def main():
                     help="auto: the fast build if it meets BASELINE's tolerance against the parity build in this run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs (N = 1 only)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "peer-static", "nccl"],
-                    help="N > 1: shared work queue + stores over NVLink peer memory (default), round 1's static deal + barrier, or NCCL gather")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-queue", "peer-static", "nccl"],
+                    help="N > 1: interleaved items + stores over NVLink peer memory + arrival flags (default); the same with one shared "
+                         "work queue; round 1's static tiles + barrier; NCCL gather")
     ap.add_argument("--workload", default="mandelbulb4k", choices=["mandelbulb4k", "julia8k"],
                     help="mandelbulb4k = BASELINE's headline metric (default); julia8k = BASELINE configs[4]")
     args = ap.parse_args()

@@ -242,20 +242,25 @@ int  rmdf_counters_reset(rmdf_ctx *ctx);
  * reach — allocate it on rank 0 with rmdf_shared_alloc next to the frame buffer, map it elsewhere with
  * rmdf_shared_open.  Word 0 = work queue, word 1 = "go", words 8+r = arrival flag of rank r.  Per frame, with a
  * sequence number seq that grows by one (start at 1):
- *   every rank   rmdf_frame_begin(ctx, ctrl, rank, world, seq, timeout_ms)   rank 0's stream zeroes the queue and publishes
- *                                                            seq; the other ranks' streams wait for it.  Arms the next
- *                                                            rmdf_render_device / rmdf_julia_device of this context:
+ *   every rank   rmdf_frame_begin(ctx, ctrl, rank, world, seq, deal, timeout_ms)   rank 0's stream zeroes the queue and
+ *                                                            publishes seq ("go"); arms this context's next
+ *                                                            rmdf_render_device / rmdf_julia_device call:
  *   every rank   rmdf_render_device(ctx, params, frame)      the SAME full-frame params on every rank (RMDF_LAYOUT_FRAME,
- *                                                            shard_count 1), `frame` = the shared buffer.  All GPUs claim
- *                                                            work items from the one queue with system-scope atomics (a
- *                                                            dynamic deal), store into the shared frame, and the last CTA
- *                                                            of each kernel publishes seq in the rank's arrival flag.
+ *                                                            shard_count 1), `frame` = the shared buffer.  Ranks != 0 first
+ *                                                            wait on their stream for "go".  RMDF_DEAL_INTERLEAVED: work
+ *                                                            item i (a 32×8-sample block) is rendered by rank i mod world
+ *                                                            through the rank's own queue — no remote atomics.
+ *                                                            RMDF_DEAL_QUEUE: all GPUs claim items from the one queue word
+ *                                                            with system-scope atomics over NVLink.  Either way the pixels
+ *                                                            are stored into the shared frame and the last CTA of each
+ *                                                            kernel publishes seq in the rank's arrival flag.
  *   rank 0       rmdf_frame_end(ctx, ctrl, world, seq, timeout_ms)   its stream waits for all arrival flags: work queued
  *                                                            behind it sees the complete frame.  No host round trip.
  * Waits give up after timeout_ms (default 10 s when <= 0); rmdf_frame_sync_status synchronises the stream and returns
  * 0, or 1 + the index of the word a wait gave up on. */
 #define RMDF_SYNC_WORDS 64
-int  rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int timeout_ms);
+enum { RMDF_DEAL_INTERLEAVED = 0, RMDF_DEAL_QUEUE = 1 };
+int  rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int deal, int timeout_ms);
 int  rmdf_frame_end(rmdf_ctx *ctx, void *ctrl_dev, int world, uint32_t seq, int timeout_ms);
 int  rmdf_frame_sync_status(rmdf_ctx *ctx, int *timed_out_word);
 

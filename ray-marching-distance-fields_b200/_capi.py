@@ -18,6 +18,7 @@ OUT_RGBA8, OUT_RGBA32F = 0, 1
 LOD_QUAD, LOD_ALWAYS_LINEAR = 0, 1
 LAYOUT_FRAME, LAYOUT_PACKED_TILES = 0, 1
 FLAG_NORMAL_CENTRAL, FLAG_CAM_ORTHO, FLAG_RAY_TRACING_TEST, FLAG_SOFT_SHADOWS = 1, 2, 4, 8
+DEAL_INTERLEAVED, DEAL_QUEUE = 0, 1
 
 EXPORTS = [
     "rmdf_create", "rmdf_destroy", "rmdf_last_error", "rmdf_ctx_last_error", "rmdf_abi_version", "rmdf_set_stream", "rmdf_sync",
@@ -111,7 +112,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_enable_peer.argtypes = [vp, C.c_int]
     L.rmdf_host_register.argtypes = [vp, vp, C.c_int64, C.POINTER(vp)]
     L.rmdf_host_unregister.argtypes = [vp, vp]
-    L.rmdf_frame_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int]
+    L.rmdf_frame_begin.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int]
     L.rmdf_frame_end.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_int]
     L.rmdf_frame_sync_status.argtypes = [vp, ip]
     for name in EXPORTS:

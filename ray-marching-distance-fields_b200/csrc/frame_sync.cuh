@@ -1,12 +1,21 @@
 // frame_sync.cuh — the work queue and the completion signal shared by the march and Julia kernels.
 //
 // One GPU: the queue counter lives in the context's own memory and nothing is signalled.
-// Several GPUs, one process each (parallel.py SharedFrame): the queue counter, a "go" word and one arrival flag per
-// rank live in a control block on rank 0 that every rank maps through CUDA IPC.  All ranks claim work items of the
-// SAME frame-wide work list from that one counter with system-scope atomics over NVLink (a dynamic deal: a GPU that
-// draws cheap items simply claims more), store their resolved pixels straight into rank 0's frame buffer, and the
-// last CTA of each rank's kernel publishes the frame's sequence number in the rank's arrival flag.  Rank 0's stream
-// then waits on the flags (wait_flags_kernel): no NCCL call and no host round trip on the data path.
+// Several GPUs, one process each (parallel.py SharedFrame): a control block on rank 0 — a work-queue word, a "go"
+// word and one arrival flag per rank — that every rank maps through CUDA IPC.  All ranks launch the SAME frame-wide
+// work list and store their resolved pixels straight into rank 0's frame buffer; the last CTA of each rank's kernel
+// publishes the frame's sequence number in the rank's arrival flag and rank 0's stream waits on the flags
+// (wait_flags_kernel): no NCCL call and no host round trip on the data path.  Who renders which item:
+//   interleaved (default)  item i belongs to rank i mod world; every rank walks its own items through its LOCAL queue.
+//                          Items are 32×8-sample blocks, neighbouring blocks cost nearly the same, so the comb of
+//                          every world-th block is an even share (measured, N = 8: see DESIGN.md §6) — and there is
+//                          not one remote atomic.
+//   shared queue           all ranks claim from the ONE queue word with system-scope atomics over NVLink (a dynamic
+//                          deal).  Measured: one address takes ~0.8 G system atomics/s from 8 GPUs — the Julia frame's
+//                          2 M claims held N = 4 and N = 8 at the same 2.7 ms, the Mandelbulb frame lost 7 % against the
+//                          static deal at N = 8 — and claiming several items at once is no way out, because a warp that
+//                          walks k neighbouring items is as slow as one k-times larger item (+8 % for k = 8 on one GPU,
+//                          profiles/r2_item_size.md).  Kept as an option.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,19 +33,17 @@ struct FrameSync {
     unsigned int *signal;              // arrival flag to publish when the last CTA has stored; nullptr = none
     unsigned int  signal_value;
     int           queue_sys;           // the queue is shared with other GPUs: claim with a system-scope atomic
-    unsigned int  batch_max;           // items per claim: 1 for a context-local queue.  A queue shared over NVLink is
-    unsigned int  batch_div;           // claimed in batches of min(batch_max, remaining / batch_div) consecutive items
-                                       // ("guided self-scheduling": big batches while the frame is far from done, single
-                                       // items at the end), because one address takes ~0.8 G system-scope atomics/s
-                                       // from 8 GPUs — measured: the Julia frame's 2 M single-item claims held N = 4 and
-                                       // N = 8 at the same 2.7 ms, and the Mandelbulb frame lost 15 % at N = 8
+    unsigned int  batch_max;           // items per claim (1; > 1 only through the RMDF_BATCH_MAX tuning override: batches of
+    unsigned int  batch_div;           // min(batch_max, remaining / batch_div) consecutive items, see the note above)
+    unsigned int  item_stride;         // interleaved deal: local item j is frame item j·item_stride + item_offset
+    unsigned int  item_offset;
 };
 
 // The warp's current batch of work items [next, end) — all members are warp-uniform.
 struct ItemBatch { unsigned next = 0, end = 0, seen = 0; };
 
-// Next work item of this warp, or a value >= n_items when the queue is drained.  Lane 0 claims a new batch when the
-// current one is used up; its size follows the progress the previous claim saw.
+// Next work item of this warp (an index into this context's own item list), or a value >= n_items when the queue is
+// drained.  Lane 0 claims a new batch when the current one is used up.
 __device__ __forceinline__ unsigned next_item(const FrameSync &S, ItemBatch &b, unsigned n_items, int lane)
 {
     if (b.next == b.end) {

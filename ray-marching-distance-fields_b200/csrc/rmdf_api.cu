@@ -54,7 +54,7 @@ struct rmdf_ctx {
     unsigned int *d_queue = nullptr;   // [0] work queue, [1] CTA-exit counter of the running kernel, [2] wait status
     // multi-GPU frame assembly (rmdf_frame_begin): applies to the next render / Julia launch, then clears
     unsigned int *sync_ctrl = nullptr;
-    int sync_rank = 0, sync_world = 1, sync_timeout_ms = 0;
+    int sync_rank = 0, sync_world = 1, sync_timeout_ms = 0, sync_deal = 0;
     unsigned int sync_seq = 0;
     unsigned long long *d_counters = nullptr;
     uint64_t launches = 0;
@@ -725,12 +725,16 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.out = fb_dev;
     mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
     mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.batch_max = 1; mp.sync.batch_div = 1;
+    mp.sync.item_stride = 1; mp.sync.item_offset = 0;
     int world = 1;
+    unsigned int *go_word = nullptr;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
         if (wl.rect_mode != 0 || p->layout != RMDF_LAYOUT_FRAME)
             return fail(RMDF_ERR_ARG, "a multi-GPU frame (rmdf_frame_begin) needs the full frame in RMDF_LAYOUT_FRAME (no tile, shard or row range)");
-        mp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; mp.sync.queue_sys = 1;
+        if (ctx->sync_deal == RMDF_DEAL_QUEUE) { mp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; mp.sync.queue_sys = 1; }
+        else { mp.sync.item_stride = (unsigned)ctx->sync_world; mp.sync.item_offset = (unsigned)ctx->sync_rank; }
         mp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; mp.sync.signal_value = ctx->sync_seq;
+        go_word = ctx->sync_ctrl + kSyncGoWord;
         world = ctx->sync_world;
         ctx->sync_ctrl = nullptr;
     }
@@ -768,15 +772,20 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
     const int64_t n_items = (int64_t)mp.blocks_x * mp.blocks_y * wl.n_tiles;
     if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
-    mp.n_items = (int)n_items;
-    if (mp.n_items == 0) return RMDF_OK;
-    if (mp.sync.queue_sys) { mp.sync.batch_max = 8u; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
+    // interleaved deal: this rank's items are offset, offset + stride, ... — the kernel walks them as local items 0..n-1
+    mp.n_items = (int)((n_items - mp.sync.item_offset + mp.sync.item_stride - 1) / mp.sync.item_stride);
+    if (n_items <= (int64_t)mp.sync.item_offset) mp.n_items = 0;
+    if (const char *e = getenv("RMDF_BATCH_MAX")) {         // tuning override (experiments only)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) { mp.sync.batch_max = (unsigned)v; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
+    }
+    if (mp.n_items == 0 && mp.sync.signal == nullptr) return RMDF_OK;
     int grid = ctas_per_sm * ctx->sm_count;
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (grid > need) grid = need;
+    if (grid > need) grid = need > 0 ? need : 1;             // a rank without items still publishes its arrival flag
 
-    if (mp.sync.queue_sys && ctx->sync_rank != 0) {        // rank != 0 of a multi-GPU frame: wait for rank 0's "go" (see rmdf_frame_begin)
-        cudaError_t ew = launch_wait_flags(mp.sync.queue - kSyncQueueWord + kSyncGoWord, 1, mp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
+    if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go" (see rmdf_frame_begin)
+        cudaError_t ew = launch_wait_flags(go_word, 1, mp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
                                            ctx->d_queue + 2, ctx->stream);
         if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
         ctx->launches++;
@@ -874,6 +883,7 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->out_stride = w >> k;
     jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
     jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.batch_max = 1; jp->sync.batch_div = 1;
+    jp->sync.item_stride = 1; jp->sync.item_offset = 0;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
 }
@@ -882,21 +892,28 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
 {
     jp.out = (uint32_t *)fb_dev;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    unsigned int *go_word = nullptr;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
         if (jp.shard_count != 1 || !jp.frame_layout || jp.y0 != 0 || jp.y1 != jp.h) {
             ctx->sync_ctrl = nullptr;
             return fail(RMDF_ERR_ARG, "a multi-GPU Julia frame (rmdf_frame_begin) needs the whole frame, one band list, frame layout");
         }
-        jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1;
+        if (ctx->sync_deal == RMDF_DEAL_QUEUE) { jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1; }
+        else {
+            jp.sync.item_stride = (unsigned)ctx->sync_world; jp.sync.item_offset = (unsigned)ctx->sync_rank;
+            const int all = jp.n_items;
+            jp.n_items = all > ctx->sync_rank ? (all - ctx->sync_rank + ctx->sync_world - 1) / ctx->sync_world : 0;
+        }
         jp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; jp.sync.signal_value = ctx->sync_seq;
-        jp.sync.batch_max = 16u; jp.sync.batch_div = 4u * (unsigned)(julia_ctas_per_sm() * ctx->sm_count * kWarpsPerCta * ctx->sync_world);
+        go_word = ctx->sync_ctrl + kSyncGoWord;
         ctx->sync_ctrl = nullptr;
     }
+    if (jp.n_items == 0 && jp.sync.signal == nullptr) return RMDF_OK;
     int grid = julia_ctas_per_sm() * ctx->sm_count;
     const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (grid > need) grid = need;
-    if (jp.sync.queue_sys && ctx->sync_rank != 0) {        // rank != 0 of a multi-GPU frame: wait for rank 0's "go"
-        cudaError_t ew = launch_wait_flags(jp.sync.queue - kSyncQueueWord + kSyncGoWord, 1, jp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
+    if (grid > need) grid = need > 0 ? need : 1;
+    if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go"
+        cudaError_t ew = launch_wait_flags(go_word, 1, jp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
                                            ctx->d_queue + 2, ctx->stream);
         if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
         ctx->launches++;
@@ -1038,10 +1055,11 @@ extern "C" int rmdf_host_unregister(rmdf_ctx *ctx, void *host_ptr)
 }
 
 // ---- one frame over several GPUs: shared work queue + arrival flags in peer memory (csrc/frame_sync.cuh) --------
-extern "C" int rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int timeout_ms)
+extern "C" int rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int world, uint32_t seq, int deal, int timeout_ms)
 {
     DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if (!ctrl_dev || world < 1 || world > 32 || rank < 0 || rank >= world) return fail(RMDF_ERR_ARG, "rmdf_frame_begin: bad arguments (rank %d of %d)", rank, world);
+    if (deal != RMDF_DEAL_INTERLEAVED && deal != RMDF_DEAL_QUEUE) return fail(RMDF_ERR_ARG, "rmdf_frame_begin: deal %d unknown", deal);
     if (timeout_ms <= 0) timeout_ms = 10000;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     unsigned int *ctrl = (unsigned int *)ctrl_dev;
@@ -1053,7 +1071,7 @@ extern "C" int rmdf_frame_begin(rmdf_ctx *ctx, void *ctrl_dev, int rank, int wor
     // The other ranks wait for "go" on their stream — but that wait kernel is enqueued by the render call itself, after
     // it has made sure its own kernel is loaded: CUDA loads kernels lazily and a first load can need the device to
     // drain, which a spinning wait kernel would hold up until its time-out.
-    ctx->sync_ctrl = ctrl; ctx->sync_rank = rank; ctx->sync_world = world; ctx->sync_seq = seq; ctx->sync_timeout_ms = timeout_ms;
+    ctx->sync_ctrl = ctrl; ctx->sync_rank = rank; ctx->sync_world = world; ctx->sync_seq = seq; ctx->sync_timeout_ms = timeout_ms; ctx->sync_deal = deal;
     return RMDF_OK;
 }
 extern "C" int rmdf_frame_end(rmdf_ctx *ctx, void *ctrl_dev, int world, uint32_t seq, int timeout_ms)

@@ -406,9 +406,9 @@ class ShaderRenderer:
     def sharedClose(self, ptr: int) -> None:
         check(self._lib.rmdf_shared_close(self._h, C.c_void_p(ptr)))
 
-    def frameBegin(self, ctrl_ptr: int, rank: int, world: int, seq: int, timeout_ms: int = 10000) -> None:
+    def frameBegin(self, ctrl_ptr: int, rank: int, world: int, seq: int, timeout_ms: int = 10000, deal: int = _capi.DEAL_INTERLEAVED) -> None:
         """One frame over several GPUs (include/rmdf.h rmdf_frame_begin): arms this context's next render."""
-        check(self._lib.rmdf_frame_begin(self._h, C.c_void_p(ctrl_ptr), rank, world, seq, timeout_ms))
+        check(self._lib.rmdf_frame_begin(self._h, C.c_void_p(ctrl_ptr), rank, world, seq, deal, timeout_ms))
 
     def frameEnd(self, ctrl_ptr: int, world: int, seq: int, timeout_ms: int = 10000) -> None:
         check(self._lib.rmdf_frame_end(self._h, C.c_void_p(ctrl_ptr), world, seq, timeout_ms))

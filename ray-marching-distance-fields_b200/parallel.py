@@ -138,11 +138,12 @@ class SharedFrame:
     as the render target, so the kernels' 128-bit stores cross NVLink while the rest of the frame is still being
     marched.  Behind the frame sits a control block (work queue, "go" word, one arrival flag per rank):
 
-      static deal   renderDevice(params with shard_rank/shard_count, self.ptr); complete()   — one barrier
-      dynamic deal  begin(); renderDevice(the SAME full-frame params on every rank, self.ptr); end()
-                    all GPUs claim work items from ONE queue with system-scope atomics over NVLink (a GPU that draws
-                    cheap items claims more), each kernel's last CTA publishes the frame number in its rank's arrival
-                    flag, and rank 0's stream waits on the flags: no NCCL call, no host round trip on the data path.
+      tiles + barrier  renderDevice(params with shard_rank/shard_count, self.ptr); complete()   — round 1: one NCCL barrier
+      flags            begin(); renderDevice(the SAME full-frame params on every rank, self.ptr); end()
+                       work item i (a 32×8-sample block) belongs to rank i mod world (or, deal = 1, all GPUs claim items
+                       from ONE queue with system-scope atomics over NVLink); each kernel's last CTA publishes the frame
+                       number in its rank's arrival flag and rank 0's stream waits on the flags: no NCCL call, no host
+                       round trip on the data path.
     """
 
     def __init__(self, sr, n_words: int, world: int, rank: int):
@@ -161,10 +162,11 @@ class SharedFrame:
         self.ctrl = self.ptr + frame_bytes
 
     # -- dynamic deal ---------------------------------------------------------------------------------
-    def begin(self, timeout_ms: int = 10000) -> int:
-        """Every rank, before its render call of the frame.  Returns the frame's sequence number."""
+    def begin(self, timeout_ms: int = 10000, deal: int = 0) -> int:
+        """Every rank, before its render call of the frame.  deal: 0 = interleaved (item i → rank i mod world, local
+        queues), 1 = one shared queue claimed over NVLink.  Returns the frame's sequence number."""
         self.seq += 1
-        self.sr.frameBegin(self.ctrl, self.rank, self.world, self.seq, timeout_ms)
+        self.sr.frameBegin(self.ctrl, self.rank, self.world, self.seq, timeout_ms, deal)
         return self.seq
 
     def end(self, timeout_ms: int = 10000) -> None:

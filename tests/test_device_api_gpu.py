@@ -149,13 +149,15 @@ def _view_i32(ptr, n):
     return torch.as_tensor(w, device="cuda:0")
 
 
+@pytest.mark.parametrize("deal", [0, 1])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
+def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world, deal):
     """include/rmdf.h rmdf_frame_begin / rmdf_frame_end (csrc/frame_sync.cuh): `world` contexts on ONE device play
     the ranks of a multi-GPU frame — one control block, one frame buffer, every context launches the SAME full-frame
     work list, the kernels (concurrent, on their own streams) claim items from the one queue, the last CTA of each
     publishes the frame number, rank 0's stream waits for all arrival flags.  The frame must be bit-identical to a
-    plain render, every sample rendered exactly once, for consecutive frames and for the Julia kernel too."""
+    plain render, every sample rendered exactly once, for consecutive frames and for the Julia kernel too.
+    deal 0 = interleaved (item i → rank i mod world, local queues), 1 = the one shared queue."""
     import torch
     w, h, k = 1024, 512, 1
     n_out = (w >> k) * (h >> k)
@@ -174,7 +176,7 @@ def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
             for r in srs:
                 r.resetCounters()
             for rank in reversed(range(world)):               # the waiting ranks first: rank 0's "go" must still get through
-                srs[rank].frameBegin(ctrl, rank, world, seq, 5000)
+                srs[rank].frameBegin(ctrl, rank, world, seq, 5000, deal)
                 srs[rank].renderDevice(p, ptr)
             srs[0].frameEnd(ctrl, world, seq, 5000)
             assert srs[0].frameSyncStatus() == 0              # synchronises rank 0's stream: the frame is complete
@@ -182,12 +184,15 @@ def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
             assert np.array_equal(got, want), seq
             for r in srs[1:]:
                 assert r.frameSyncStatus() == 0
-            assert sum(r.counters()["samples"] for r in srs) == w * h          # every sample exactly once
+            cs = [r.counters()["samples"] for r in srs]
+            assert sum(cs) == w * h                                            # every sample exactly once
+            if deal == 0:
+                assert max(cs) - min(cs) <= 32 * 8 * 2                         # interleaved: equal shares to within an item or two
         # Julia through the same protocol
         jw, jh = w, h                                         # the same output size: the shared buffer holds n_out words
         wantj = srs[0].juliaAnimated(jw, jh, None, False, 7.0, resolve_log2=k)
         for rank in reversed(range(world)):
-            srs[rank].frameBegin(ctrl, rank, world, 4, 5000)
+            srs[rank].frameBegin(ctrl, rank, world, 4, 5000, deal)
             srs[rank].juliaDevice(jw, jh, False, 7.0, (0, jh), k, ptr)
         srs[0].frameEnd(ctrl, world, 4, 5000)
         assert srs[0].frameSyncStatus() == 0
@@ -210,7 +215,8 @@ def test_shared_queue_frame_protocol_on_one_gpu(R, O, oracle_envs, world):
             r.close()
 
 
-def test_shared_queue_frame_two_gpus(R, oracle_envs):
+@pytest.mark.parametrize("deal", [0, 1])
+def test_shared_queue_frame_two_gpus(R, oracle_envs, deal):
     """The same protocol across two devices over peer memory (single process; run with gpurun --gpus 2)."""
     import torch
     if torch.cuda.device_count() < 2:
@@ -229,8 +235,8 @@ def test_shared_queue_frame_two_gpus(R, oracle_envs):
         p = a.makeParams(R.FragmentShader.FSMBPower8Shader, None, w, h, 0.0, resolve_log2=k)
         for seq in (1, 2):
             a.resetCounters(); b.resetCounters()
-            b.frameBegin(ctrl, 1, 2, seq, 5000); b.renderDevice(p, ptr)
-            a.frameBegin(ctrl, 0, 2, seq, 5000); a.renderDevice(p, ptr)
+            b.frameBegin(ctrl, 1, 2, seq, 5000, deal); b.renderDevice(p, ptr)
+            a.frameBegin(ctrl, 0, 2, seq, 5000, deal); a.renderDevice(p, ptr)
             a.frameEnd(ctrl, 2, seq, 5000)
             sa, sb = a.frameSyncStatus(), b.frameSyncStatus()
             assert (sa, sb) == (0, 0), (seq, sa, sb)
