@@ -6,10 +6,10 @@
 // work list and store their resolved pixels straight into rank 0's frame buffer; the last CTA of each rank's kernel
 // publishes the frame's sequence number in the rank's arrival flag and rank 0's stream waits on the flags
 // (wait_flags_kernel): no NCCL call and no host round trip on the data path.  Who renders which item:
-//   interleaved (default)  item i belongs to rank i mod world; every rank walks its own items through its LOCAL queue.
-//                          Items are 32×8-sample blocks, neighbouring blocks cost nearly the same, so the comb of
-//                          every world-th block is an even share (measured, N = 8: see DESIGN.md §6) — and there is
-//                          not one remote atomic.
+//   interleaved (default)  groups of a few x-adjacent items are dealt round-robin (group g belongs to rank g mod world);
+//                          every rank walks its own items through its LOCAL queue.  Items are 32×8-sample blocks,
+//                          neighbouring blocks cost nearly the same, so the comb of every world-th group is an even
+//                          share (measured, N = 8: see DESIGN.md §6) — and there is not one remote atomic.
 //   shared queue           all ranks claim from the ONE queue word with system-scope atomics over NVLink (a dynamic
 //                          deal).  Measured: one address takes ~0.8 G system atomics/s from 8 GPUs — the Julia frame's
 //                          2 M claims held N = 4 and N = 8 at the same 2.7 ms, the Mandelbulb frame lost 7 % against the
@@ -35,9 +35,20 @@ struct FrameSync {
     int           queue_sys;           // the queue is shared with other GPUs: claim with a system-scope atomic
     unsigned int  batch_max;           // items per claim (1; > 1 only through the RMDF_BATCH_MAX tuning override: batches of
     unsigned int  batch_div;           // min(batch_max, remaining / batch_div) consecutive items, see the note above)
-    unsigned int  item_stride;         // interleaved deal: local item j is frame item j·item_stride + item_offset
-    unsigned int  item_offset;
+    unsigned int  item_stride;         // interleaved deal, in groups of item_group x-adjacent items: local item j = (q, m) with
+    unsigned int  item_offset;         // q = j / item_group, m = j mod item_group is frame item (q·item_stride + item_offset)·
+    unsigned int  item_group;          // item_group + m.  A group covers >= 128 B of every output row, so that no 64 B line of
+    unsigned int  items_total;         // a HOST frame buffer is shared by two GPUs (partial-line writes over PCIe: the end-to-
+                                       // end frame took 4.2 instead of 2.7 ms at N = 8 with single-item interleaving)
 };
+
+// local item → frame item of the interleaved deal (identity for a single GPU); >= items_total: nothing to do
+__device__ __forceinline__ unsigned frame_item(const FrameSync &S, unsigned j)
+{
+    if (S.item_stride == 1u) return j;
+    const unsigned q = j / S.item_group, m = j - q * S.item_group;
+    return (q * S.item_stride + S.item_offset) * S.item_group + m;
+}
 
 // The warp's current batch of work items [next, end) — all members are warp-uniform.
 struct ItemBatch { unsigned next = 0, end = 0, seen = 0; };

@@ -117,7 +117,9 @@ julia_kernel(const JuliaParams P)
         if (item >= (unsigned)P.n_items) break;
         // item → (band of this rank, block row inside the band, block column)
         const int per_band = P.blocks_x * P.blocks_y;
-        const int fitem = (int)(item * P.sync.item_stride + P.sync.item_offset);      // interleaved multi-GPU deal (frame_sync.cuh)
+        const unsigned fi = frame_item(P.sync, item);                                  // interleaved multi-GPU deal (frame_sync.cuh)
+        if (fi >= P.sync.items_total) continue;
+        const int fitem = (int)fi;
         const int band_k = fitem / per_band, in_band = fitem - band_k * per_band;
         const int by = in_band / P.blocks_x, bx = in_band - by * P.blocks_x;
         const int band = band_k * P.shard_count + P.shard_rank;

@@ -725,7 +725,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.out = fb_dev;
     mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
     mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.batch_max = 1; mp.sync.batch_div = 1;
-    mp.sync.item_stride = 1; mp.sync.item_offset = 0;
+    mp.sync.item_stride = 1; mp.sync.item_offset = 0; mp.sync.item_group = 1; mp.sync.items_total = 0;
     int world = 1;
     unsigned int *go_word = nullptr;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
@@ -772,9 +772,19 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
     const int64_t n_items = (int64_t)mp.blocks_x * mp.blocks_y * wl.n_tiles;
     if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
-    // interleaved deal: this rank's items are offset, offset + stride, ... — the kernel walks them as local items 0..n-1
-    mp.n_items = (int)((n_items - mp.sync.item_offset + mp.sync.item_stride - 1) / mp.sync.item_stride);
-    if (n_items <= (int64_t)mp.sync.item_offset) mp.n_items = 0;
+    mp.n_items = (int)n_items;
+    mp.sync.items_total = (unsigned)n_items;
+    if (mp.sync.item_stride > 1) {
+        // interleaved deal: groups of x-adjacent items that cover >= 128 B of an output row go round-robin to the ranks;
+        // the kernel walks this rank's groups as local items 0 .. n-1 (frame_sync.cuh frame_item)
+        const int out_bytes_per_item_row = (mp.item_w >> p->resolve_log2) * ((p->out_format == RMDF_OUT_RGBA32F) ? 16 : 4);
+        int g = 1;
+        while (g * out_bytes_per_item_row < 128 && g * 2 <= mp.blocks_x) g *= 2;
+        mp.sync.item_group = (unsigned)g;
+        const int64_t n_groups = (n_items + g - 1) / g;
+        const int64_t mine = n_groups > mp.sync.item_offset ? (n_groups - mp.sync.item_offset + mp.sync.item_stride - 1) / mp.sync.item_stride : 0;
+        mp.n_items = (int)(mine * g);
+    }
     if (const char *e = getenv("RMDF_BATCH_MAX")) {         // tuning override (experiments only)
         const int v = atoi(e);
         if (v >= 1 && v <= 64) { mp.sync.batch_max = (unsigned)v; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
@@ -883,7 +893,7 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->out_stride = w >> k;
     jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
     jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.batch_max = 1; jp->sync.batch_div = 1;
-    jp->sync.item_stride = 1; jp->sync.item_offset = 0;
+    jp->sync.item_stride = 1; jp->sync.item_offset = 0; jp->sync.item_group = 1; jp->sync.items_total = 0;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
 }
@@ -892,6 +902,7 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
 {
     jp.out = (uint32_t *)fb_dev;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    jp.sync.items_total = (unsigned)jp.n_items;
     unsigned int *go_word = nullptr;
     if (ctx->sync_ctrl) {                                   // armed by rmdf_frame_begin: one frame over several GPUs
         if (jp.shard_count != 1 || !jp.frame_layout || jp.y0 != 0 || jp.y1 != jp.h) {
@@ -901,8 +912,12 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
         if (ctx->sync_deal == RMDF_DEAL_QUEUE) { jp.sync.queue = ctx->sync_ctrl + kSyncQueueWord; jp.sync.queue_sys = 1; }
         else {
             jp.sync.item_stride = (unsigned)ctx->sync_world; jp.sync.item_offset = (unsigned)ctx->sync_rank;
-            const int all = jp.n_items;
-            jp.n_items = all > ctx->sync_rank ? (all - ctx->sync_rank + ctx->sync_world - 1) / ctx->sync_world : 0;
+            int g = 1;                                      // groups of x-adjacent 32-sample items covering >= 128 B of an output row
+            while (g * ((kBlockDim >> jp.resolve_log2) * 4) < 128 && g * 2 <= jp.blocks_x) g *= 2;
+            jp.sync.item_group = (unsigned)g;
+            const int n_groups = (jp.n_items + g - 1) / g;
+            const int mine = n_groups > ctx->sync_rank ? (n_groups - ctx->sync_rank + ctx->sync_world - 1) / ctx->sync_world : 0;
+            jp.n_items = mine * g;
         }
         jp.sync.signal = ctx->sync_ctrl + kSyncFlagWord0 + ctx->sync_rank; jp.sync.signal_value = ctx->sync_seq;
         go_word = ctx->sync_ctrl + kSyncGoWord;
