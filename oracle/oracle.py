@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py; the product package never
-imports this module.  PARITY STATUS: "parity unpinned" (see oracle_march.c).
+imports this module.  PARITY STATUS: the shader half is pinned by oracle/_ref (oracle_ref.py,
+oracle_march.c); the Haskell half (oracle_envmap.c, oracle_julia.c) is "parity unpinned".
 """
 from __future__ import annotations
 

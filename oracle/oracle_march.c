@@ -6,12 +6,12 @@
  * cpu_baseline / --impl reference legs may load this library; the product
  * (librmdf_b200.so) never links, loads or calls it.
  *
- * PARITY STATUS: "parity unpinned" — the reference ships no tests, golden images
- * or known-answer vectors, and neither GHC nor any OpenGL
- * implementation exists in this image, so the reference itself cannot be run.
- * The oracle is pinned only by the reference's source text plus the OpenGL 3.3
- * fixed-function rules listed in SURVEY.md Appendix A; its own known-answer
- * vectors live in tests/golden/ (generated by tests/golden/make_golden.py).
+ * PARITY STATUS: PINNED by oracle/_ref — the reference's own fragment.shd compiled by g++
+ * (oracle/ref/, `make -C oracle ref`): every function below and whole frames per shader
+ * variant are bit-identical to that compiled shader (tests/test_ref_shader_cpu.py), and
+ * tests/golden/ref_shader.npz carries its outputs to the GPU box.  What stays a convention
+ * is the platform around the shader (GLSL built-ins, GL sampler: C0-C6 below), which the
+ * compiled shader shares through oracle/ref/glsl_compat.hpp.
  *
  * GLSL built-ins come from include/rmdf_glsl.h (deterministic IEEE-only
  * definitions); compile with -ffp-contract=off and without -ffast-math.

@@ -7,19 +7,9 @@
 //   pack_half4_kernel the GL RGB16F upload,    HDREnvMap.hs:160-161
 //   mip_kernel        glGenerateMipmap chain,  FrameBuffer.hs:153-154
 //
-// Convolution design (FP32-FMA bound, ~28 instructions per (dst,src) pair, all four
-// powers from one cosine):
-//   * CTA = 32 destination columns × 8 destination rows; the 32×256 slice of the
-//     reference's per-pixel cos|φ_L−φ_x| lookup (HDREnvMap.hs:230) is computed ONCE
-//     on the host with the same libm calls and kept in 32 KB of shared memory, so
-//     `cosAngle` is bit-identical to the reference's and the `cosAngle > 0` sample
-//     count n matches exactly;
-//   * source rows are staged through shared memory as float4 (rgb·sinθ_P, pad) and
-//     read as 128-bit warp broadcasts;
-//   * powers {1,8,64,512} (ShaderRendering.hs:71) come from nine squarings of the
-//     cosine — no pow() in the loop (the reference's own TODO, HDREnvMap.hs:245-246);
-//   * the 128 source rows are split over gridDim.z CTAs; partial sums are reduced in
-//     a fixed order by a second tiny kernel (deterministic, no float atomics).
+// Convolution design: see the comment above convolve_kernel (persistent grid over dynamic chunks, exact skipping of
+// the half of the pairs that lie behind the lobe, the reference's φ table in shared memory, powers {1,8,64,512} from
+// nine squarings, packed FP32 accumulators, deterministic finish pass).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
