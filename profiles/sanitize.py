@@ -21,4 +21,30 @@ with R.ShaderRenderer(0) as sr:
     sr.drawShaderTile(2, None, 128, 64, 1.0, shard_rank=1, shard_count=2, layout=R.LAYOUT_PACKED_TILES, resolve_log2=2)
     sr.juliaAnimated(97, 33, None, True, 3.0)
     sr.juliaAnimated(128, 64, None, False, 3.0, resolve_log2=3)
+    # round 2: tiles of a frame whose size is not a multiple of 16 (helper quads, clipped stores), soft shadows,
+    # a ragged convolution, and the multi-GPU frame protocol with two contexts on this GPU (both deals, march + Julia)
+    for idx in (0, 9, 27, 63):
+        sr.drawShaderTile(1, idx, 100, 45, 1.0)
+        sr.drawShaderTile(1, idx, 100, 45, 1.0, layout=R.LAYOUT_PACKED_TILES, out_format=R.OUT_RGBA32F)
+    sr.drawShaderTile(2, None, 64, 48, 1.0, flags=R.FLAG_SOFT_SHADOWS, mode=1)
+    sr.cosineConvolveHDREnvMapSweep(sr.resizeHDRImage(refl, 48), [1.0, 8.0, 64.0, 512.0, 3.0])
+    with R.ShaderRenderer(0) as b:
+        w, h, k = 128, 64, 1
+        n_out = (w >> k) * (h >> k)
+        fb = (n_out * 4 + 255) & ~255
+        ptr, _ = sr.sharedAlloc(fb + 256)
+        p = sr.makeParams(2, None, w, h, 1.0, resolve_log2=k, mode=1)
+        seq = 0
+        for deal in (0, 1):
+            seq += 1
+            b.frameBegin(ptr + fb, 1, 2, seq, 3000, deal); b.renderDevice(p, ptr)
+            sr.frameBegin(ptr + fb, 0, 2, seq, 3000, deal); sr.renderDevice(p, ptr)
+            sr.frameEnd(ptr + fb, 2, seq, 3000)
+            assert sr.frameSyncStatus() == 0 and b.frameSyncStatus() == 0
+            seq += 1
+            b.frameBegin(ptr + fb, 1, 2, seq, 3000, deal); b.juliaDevice(w, h, False, 3.0, (0, h), k, ptr)
+            sr.frameBegin(ptr + fb, 0, 2, seq, 3000, deal); sr.juliaDevice(w, h, False, 3.0, (0, h), k, ptr)
+            sr.frameEnd(ptr + fb, 2, seq, 3000)
+            assert sr.frameSyncStatus() == 0 and b.frameSyncStatus() == 0
+        b.sync(); sr.sharedFree(ptr)
     print("sanitize workload done", sr.counters()["launches"], "launches")
