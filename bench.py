@@ -205,9 +205,10 @@ def oracle_env_cubes(O):
     return [O.latlong_to_cube(img)] + [O.latlong_to_cube(O.rgbe_roundtrip(O.convolve(small, p))) for p in (1.0, 8.0, 64.0, 512.0)]
 
 
-def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12"))):
+def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float(os.environ.get("RMDF_BENCH_CPU_BUDGET_S", "12")), keep=None):
     """Times the CPU implementation on a bounded, frame-covering sample of config 4: a 16×9 grid of
-    square crops spread uniformly over the 15360×8640 frame buffer, all host threads."""
+    square crops spread uniformly over the 15360×8640 frame buffer, all host threads.
+    keep: a list that receives (rect, RGBA8 words) of every 9th crop of the last step, for the in-run parity check."""
     O, B, kind = cpu_backend()
     envs = oracle_env_cubes(O)
     cores = O.host_threads()
@@ -220,8 +221,10 @@ def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float
                 cx = (FB_W // 16) * gx + FB_W // 32
                 cy = (FB_H // 9) * gy + FB_H // 18
                 x0, y0 = (cx - crop // 2) & ~1, (cy - crop // 2) & ~1
-                B.render(SCENE_MB_POWER8, FB_W, FB_H, TIME, envs=envs, rect=(x0, y0, x0 + crop, y0 + crop), want_linear=False,
-                         threads=cores, lod_policy=pol)
+                r = B.render(SCENE_MB_POWER8, FB_W, FB_H, TIME, envs=envs, rect=(x0, y0, x0 + crop, y0 + crop), want_linear=False,
+                             threads=cores, lod_policy=pol)
+                if keep is not None and (gy * 16 + gx) % 9 == 4:
+                    keep.append(((x0, y0, x0 + crop, y0 + crop), r["fb"]))
                 n += crop * crop
         return n, time.perf_counter() - t0
 
@@ -232,10 +235,12 @@ def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float
         run(crop)
     times, n = [], 0
     for _ in range(max(1, steps)):
+        if keep is not None:
+            del keep[:]
         n, dt = run(crop)
         times.append(dt)
     dt = float(np.mean(times))
-    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind, "lod_policy": pol,
             "sample": "144 crops of %dx%d samples on a 16x9 grid over the 15360x8640 frame buffer (%.2f%% of the frame); %s"
                       % (crop, crop, 100.0 * n / (FB_W * FB_H), cpu_kind_note(kind)),
             "seconds_per_step": dt, "samples_per_step": n}
@@ -529,8 +534,23 @@ def run_ours(args):
         if other is not None:
             line["other_mode"] = other
         if world == 1 and not args.no_cpu_baseline:
-            b = cpu_baseline_sample()
+            kept = []
+            b = cpu_baseline_sample(keep=kept)
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # parity in this very run, at the real frame size: the CPU leg's pixels (the reference's shader compiled by
+            # g++ when kind = "reference") against the CUDA parity build's unresolved frame, same filtering policy
+            pp = sr.makeParams(scene, None, FB_W, FB_H, TIME, mode=R.MODE_PARITY, lod_policy=b["lod_policy"])
+            lvl0 = torch.empty(FB_W * FB_H, dtype=torch.int32, device=dev)
+            sr.renderDevice(pp, lvl0.data_ptr()); torch.cuda.synchronize()
+            frame0 = lvl0.reshape(FB_H, FB_W)
+            bad = tot = 0
+            for (x0, y0, x1, y1), want in kept:
+                got = frame0[y0:y1, x0:x1].cpu().numpy().view(np.uint32)
+                bad += int((got != want).sum()); tot += want.size
+            del lvl0, frame0
+            line["parity_check"] = {"against": "cpu_baseline kind '%s' (reference = /root/reference/fragment.shd compiled by g++, oracle/_ref)" % b["kind"],
+                                    "what": "RGBA8 words of the CUDA parity build, unresolved 15360x8640 frame buffer, %d crops spread over the frame" % len(kept),
+                                    "samples_compared": tot, "samples_differing": bad, "bit_identical": bool(tot > 0 and bad == 0)}
         if world == 1 and not args.no_configs:
             # the other BASELINE configs (1, 2, 3, 5) and the fourth scene, a few hundred ms of GPU time in all
             import bench_configs
