@@ -240,7 +240,7 @@ def cpu_baseline_sample(steps: int = 1, warmup: int = 0, budget_s: float = float
         n, dt = run(crop)
         times.append(dt)
     dt = float(np.mean(times))
-    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind, "lod_policy": pol,
+    return {"value": n / dt, "unit": "samples/s", "cores": cores, "kind": kind, "lod_policy": pol, "envs": envs,
             "sample": "144 crops of %dx%d samples on a 16x9 grid over the 15360x8640 frame buffer (%.2f%% of the frame); %s"
                       % (crop, crop, 100.0 * n / (FB_W * FB_H), cpu_kind_note(kind)),
             "seconds_per_step": dt, "samples_per_step": n}
@@ -539,9 +539,13 @@ def run_ours(args):
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
             # parity in this very run, at the real frame size: the CPU leg's pixels (the reference's shader compiled by
             # g++ when kind = "reference") against the CUDA parity build's unresolved frame, same filtering policy
+            # (the CPU leg's own cube maps are bound for this: the GPU-built ones differ from them in the last bits of some
+            # texels — convolution summation order, CUDA vs glibc acosf — which is a property of the prefilter)
             pp = sr.makeParams(scene, None, FB_W, FB_H, TIME, mode=R.MODE_PARITY, lod_policy=b["lod_policy"])
             lvl0 = torch.empty(FB_W * FB_H, dtype=torch.int32, device=dev)
+            sr.bindCubeMaps(range(5), b["envs"])
             sr.renderDevice(pp, lvl0.data_ptr()); torch.cuda.synchronize()
+            sr.bindCubeMaps(range(5), cubes)
             frame0 = lvl0.reshape(FB_H, FB_W)
             bad = tot = 0
             for (x0, y0, x1, y1), want in kept:
