@@ -41,7 +41,7 @@ static int fail(int code, const char *fmt, ...)
 struct EnvSlot {
     int face_w = 0;
     cudaArray_t arr_layered = nullptr, arr_cube = nullptr;
-    cudaTextureObject_t tex_point = 0, tex_cube = 0;
+    cudaTextureObject_t tex_point = 0, tex_cube = 0, tex_cube_nearest = 0;
     float *faces_dev = nullptr;        // 6·w·w·3 half-rounded floats (for rmdf_envmap_get_cube)
     void *half4_dev = nullptr;         // 6·w·w half4 staging for the array copies
 };
@@ -171,6 +171,7 @@ static void free_slot(EnvSlot &s)
 {
     if (s.tex_point) cudaDestroyTextureObject(s.tex_point);
     if (s.tex_cube) cudaDestroyTextureObject(s.tex_cube);
+    if (s.tex_cube_nearest) cudaDestroyTextureObject(s.tex_cube_nearest);
     if (s.arr_layered) cudaFreeArray(s.arr_layered);
     if (s.arr_cube) cudaFreeArray(s.arr_cube);
     if (s.faces_dev) cudaFree(s.faces_dev);
@@ -350,6 +351,11 @@ static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *fa
             rd.res.array.array = s.arr_cube;
             td.filterMode = cudaFilterModeLinear; td.normalizedCoords = 1; td.seamlessCubemap = 1;
             e = cudaCreateTextureObject(&s.tex_cube, &rd, &td, nullptr);
+        }
+        if (e == cudaSuccess) {
+            // the same cube map with NEAREST (the GL minification filter, GLHelpers.hs:105-106): fast path of minified quads
+            td.filterMode = cudaFilterModePoint; td.seamlessCubemap = 0;
+            e = cudaCreateTextureObject(&s.tex_cube_nearest, &rd, &td, nullptr);
         }
     }
     if (e != cudaSuccess) {
@@ -719,6 +725,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     for (int s = 0; s < RMDF_ENV_SLOTS; s++) {
         mp.env_point[s] = ctx->env[s].tex_point;
         mp.env_cube[s] = ctx->env[s].tex_cube;
+        mp.env_cube_nearest[s] = ctx->env[s].tex_cube_nearest;
         mp.env_face[s] = ctx->env[s].face_w;
     }
     mp.cornell = ctx->d_cornell;

@@ -44,6 +44,7 @@ struct MarchParams {
     // resources
     cudaTextureObject_t env_point[5]; // layered 2D half4, point sampled (parity path)
     cudaTextureObject_t env_cube[5];  // cube map half4, linear + seamless (fast path)
+    cudaTextureObject_t env_cube_nearest[5];  // cube map half4, point sampled (fast path, minified quads)
     int   env_face[5];                // face width, 0 = unbound (samples as constant 1.0)
     const float4 *cornell;            // kCornellF4 float4 (precomputed triangle terms)
     void *out;
