@@ -25,6 +25,7 @@ struct MarchParams {
     float cam[12];                    // x̂, ŷ, ẑ, eye  (lookat, fragment.shd:829-838)
     float power;                      // animated Mandelbulb power (fragment.shd:116-119)
     float bsphere_r;                  // fragment.shd:640-649
+    float opaque_zero;                // always 0.0f: a zero the compiler cannot fold or re-materialise (fast power-8 loop)
     int   lod_policy, resolve_log2, out_format, layout;
     int   flags;                      // RMDF_FLAG_* (0 = the reference's build)
     // work list: the whole frame (0), one tile of the reference's 8×8 grid (1), or this rank's
