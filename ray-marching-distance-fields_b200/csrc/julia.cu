@@ -42,14 +42,17 @@ __device__ __forceinline__ float div_known(float a, float b, float y)
     return __fmaf_rn(__fmaf_rn(-b, q, a), y, q);
 }
 template <bool SMOOTH>
-__device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2, float rcp_log_2, const uint32_t *lut)
+__device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2, float rcp_log_2, uint32_t lut)
 {
     if (SMOOTH && iter != 40) {
         const float v = (float)iter - div_known(rg_log(rg_log(mag2)), log_2, rcp_log_2);
         const float ic = v > 0.0f ? v : 0.0f;
         return ((uint32_t)(int)truncf(div_known(ic, 40.0f, 0.025f) * 255.0f)) << 8;
     }
-    return lut[iter];
+    // lut = shared-space address of the table: one LEA + LDS (indexing the __shared__ array re-derived its window base per use)
+    uint32_t w;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(lut + 4u * (uint32_t)iter));
+    return w;
 }
 
 // One orbit step for both slots (go, Fractal2D.hs:85-90): the escape test comes first; `it` is the
@@ -91,7 +94,10 @@ __device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2
 #define RMDF_JULIA_BLOCK(b) RMDF_JULIA_STEP(b) RMDF_JULIA_STEP((b) + 1) RMDF_JULIA_STEP((b) + 2) RMDF_JULIA_STEP((b) + 3)
 #endif
 
-template <bool SMOOTH>
+// KD: the coordinate divisions col / w and row / h (Fractal2D.hs:81-82) as correctly rounded known-divisor
+// divisions (three instructions instead of the general IEEE sequence); the host sets it when neither divisor's
+// significand is all ones (div_known's condition) — every frame size in practice.
+template <bool SMOOTH, bool KD>
 __global__ void __launch_bounds__(kCtaThreads, 8)
 julia_kernel(const JuliaParams P)
 {
@@ -105,6 +111,7 @@ julia_kernel(const JuliaParams P)
     __syncthreads();
     const int mx = lane & 7, my = lane >> 3;        // a warp covers 16×4 samples: lane = 2 adjacent columns of one row
     const float kNaN = __int_as_float(0x7fffffff);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
     const int k = P.resolve_log2;
     const float log_2 = rg_log(2.0f), rcp_log_2 = 1.0f / log_2;
     const f2 ji = F2(P.julia_i);
@@ -131,8 +138,10 @@ julia_kernel(const JuliaParams P)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const int col = X0 + c * 16 + 2 * mx;
-            xs[c].x = ((float)col / P.fw) * 2.9f * P.ratio - P.xshift;
-            xs[c].y = ((float)(col + 1) / P.fw) * 2.9f * P.ratio - P.xshift;
+            const float q0 = KD ? div_known((float)col, P.fw, P.rcp_fw) : (float)col / P.fw;
+            const float q1 = KD ? div_known((float)(col + 1), P.fw, P.rcp_fw) : (float)(col + 1) / P.fw;
+            xs[c].x = q0 * 2.9f * P.ratio - P.xshift;
+            xs[c].y = q1 * 2.9f * P.ratio - P.xshift;
             asm volatile("" : "+f"(xs[c].x), "+f"(xs[c].y));   // keep the values: without this ptxas re-does the IEEE divisions per sample
         }
 
@@ -141,7 +150,8 @@ julia_kernel(const JuliaParams P)
             const int ty = trow * 4;
             if (ty >= bh) break;
             const int ly = ty + my;
-            const f2 ys = F2(((float)(Y0 + ly) / P.fh) * 2.9f - 1.45f);             // :81
+            const float qy = KD ? div_known((float)(Y0 + ly), P.fh, P.rcp_fh) : (float)(Y0 + ly) / P.fh;
+            const f2 ys = F2(qy * 2.9f - 1.45f);                                    // :81
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 const int lx = c * 16 + 2 * mx;
@@ -169,9 +179,9 @@ julia_kernel(const JuliaParams P)
                         }
                     }
                 finished:
-                    w0 = julia_word<SMOOTH>(it0, m0, log_2, rcp_log_2, s_lut);
+                    w0 = julia_word<SMOOTH>(it0, m0, log_2, rcp_log_2, lut_addr);
                     iters += (unsigned)it0; samples++;
-                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, rcp_log_2, s_lut); iters += (unsigned)it1; samples++; }
+                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, rcp_log_2, lut_addr); iters += (unsigned)it1; samples++; }
                 }
                 if (live == 3u) *reinterpret_cast<uint2 *>(stage + ly * kBlockDim + lx) = make_uint2(w0, w1);
                 else if (live)  stage[ly * kBlockDim + lx] = w0;
@@ -180,12 +190,19 @@ julia_kernel(const JuliaParams P)
         __syncwarp();
         for (int l = 1; l <= k; l++) {
             const int lw = bw >> l, lh = bh >> l, h = 1 << (l - 1);
-            for (int g = lane; g < lw * lh; g += 32) {
-                int y, x;
-                if (bw == kBlockDim) { y = g >> (5 - l); x = g & (lw - 1); }        // full-width block: no division
-                else                 { y = g / lw; x = g - y * lw; }
-                uint32_t *p = stage + ((y << l) * kBlockDim + (x << l));
-                p[0] = j_box4_green(p[0], p[h], p[h * kBlockDim], p[h * kBlockDim + h]);
+            if (bw == kBlockDim) {
+                // full-width block: a lane keeps its column and walks down the rows with a constant pointer stride
+                // (32 >> l outputs per row, 1 << l rows per pass): no index arithmetic inside the loop
+                uint32_t *p = stage + (((lane >> (5 - l)) << l) * kBlockDim + ((lane & (lw - 1)) << l));
+                const int stride = kBlockDim << (2 * l);
+                for (int y = lane >> (5 - l); y < lh; y += 1 << l, p += stride)
+                    p[0] = j_box4_green(p[0], p[h], p[h * kBlockDim], p[h * kBlockDim + h]);
+            } else {
+                for (int g = lane; g < lw * lh; g += 32) {
+                    const int y = g / lw, x = g - y * lw;
+                    uint32_t *p = stage + ((y << l) * kBlockDim + (x << l));
+                    p[0] = j_box4_green(p[0], p[h], p[h * kBlockDim], p[h * kBlockDim + h]);
+                }
             }
             __syncwarp();
         }
@@ -229,16 +246,26 @@ julia_kernel(const JuliaParams P)
 
 cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s)
 {
-    if (p.smooth) julia_kernel<true><<<grid, kCtaThreads, 0, s>>>(p);
-    else          julia_kernel<false><<<grid, kCtaThreads, 0, s>>>(p);
+    if (p.known_div) {
+        if (p.smooth) julia_kernel<true, true><<<grid, kCtaThreads, 0, s>>>(p);
+        else          julia_kernel<false, true><<<grid, kCtaThreads, 0, s>>>(p);
+    } else {
+        if (p.smooth) julia_kernel<true, false><<<grid, kCtaThreads, 0, s>>>(p);
+        else          julia_kernel<false, false><<<grid, kCtaThreads, 0, s>>>(p);
+    }
     return cudaGetLastError();
 }
 int julia_ctas_per_sm()
 {
-    int n = 0, m = 0;                          // one grid size for both variants: the smaller occupancy
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, julia_kernel<false>, kCtaThreads, 0) != cudaSuccess || n < 1) n = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, julia_kernel<true>, kCtaThreads, 0) != cudaSuccess || m < 1) m = 1;
-    return n < m ? n : m;
+    int best = 1 << 30;                        // one grid size for all variants: the smallest occupancy
+    const void *fns[4] = { (const void *)julia_kernel<false, false>, (const void *)julia_kernel<true, false>,
+                           (const void *)julia_kernel<false, true>, (const void *)julia_kernel<true, true> };
+    for (int i = 0; i < 4; i++) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[i], kCtaThreads, 0) != cudaSuccess || n < 1) n = 1;
+        if (n < best) best = n;
+    }
+    return best;
 }
 
 }  // namespace rmdf

@@ -882,6 +882,12 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->band_h = band_h; jp->shard_rank = shard_rank; jp->shard_count = shard_count;
     jp->fw = (float)w; jp->fh = (float)h;
     jp->ratio = jp->fw / jp->fh;
+    jp->rcp_fw = 1.0f / jp->fw; jp->rcp_fh = 1.0f / jp->fh;      // host code is built without fast math: correctly rounded
+    {
+        uint32_t bw, bh;
+        memcpy(&bw, &jp->fw, 4); memcpy(&bh, &jp->fh, 4);
+        jp->known_div = ((bw & 0x7fffffu) != 0x7fffffu) && ((bh & 0x7fffffu) != 0x7fffffu);
+    }
     jp->xshift = 1.45f * jp->ratio;
     const int my_bands = n_bands / shard_count;
     const int ctas = julia_ctas_per_sm();

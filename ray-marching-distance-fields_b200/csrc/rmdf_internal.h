@@ -58,6 +58,8 @@ struct JuliaParams {
     int   frame_layout;                       // 1: bands land at their frame position (shared frame buffer)
     int   band_h, shard_rank, shard_count;   // rows [y0,y1) cut into bands of band_h rows; this rank renders bands b ≡ rank (mod count)
     float julia_r, julia_i, fw, fh, ratio, xshift;
+    float rcp_fw, rcp_fh;                     // RN(1/fw), RN(1/fh) for the known-divisor divisions
+    int   known_div;                          // neither fw's nor fh's significand is all ones: div_known is exact
     int   item_h, blocks_x, blocks_y, n_items;
     int   out_stride;
     uint32_t *out;
