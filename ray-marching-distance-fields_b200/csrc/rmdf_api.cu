@@ -525,6 +525,19 @@ extern "C" int rmdf_set_cornell(rmdf_ctx *ctx, const float *xyz, int nverts)
             r[7] = make_float4((float)nx, (float)ny, (float)nz, (float)-(nx * v0.x + ny * v0.y + nz * v0.z));
         }
     }
+    // one plane test for the two triangles of a quad (CornellBox.hs builds every quad as triangles 2k, 2k+1): the
+    // pair's plane is triangle 2k's when all six vertices lie within 1e-6 of it (the culling margin is 1e-4),
+    // else the null plane, whose distance 0 never culls — the per-triangle tests still follow (culling only)
+    for (int k = 0; k < kCornellPairs; k++) {
+        const float4 pl = tab[(2 * k) * kCornellStride + 7];
+        bool coplanar = (pl.x != 0.0f || pl.y != 0.0f || pl.z != 0.0f);
+        for (int j = 0; j < 6 && coplanar; j++) {
+            const float *q = xyz + (2 * k) * 9 + j * 3;
+            const double d = (double)pl.x * q[0] + (double)pl.y * q[1] + (double)pl.z * q[2] + (double)pl.w;
+            if (!(fabs(d) <= 1.0e-6)) coplanar = false;
+        }
+        tab[32 * kCornellStride + k] = coplanar ? pl : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(ctx->d_cornell, tab, sizeof tab, cudaMemcpyHostToDevice));

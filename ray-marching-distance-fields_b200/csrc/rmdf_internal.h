@@ -14,7 +14,8 @@ constexpr int kBlockDim     = 32;    // a work item is a 32×32 block of frame-b
 constexpr int kWarpsPerCta  = RMDF_WARPS_PER_CTA;
 constexpr int kCtaThreads   = kWarpsPerCta * 32;
 constexpr int kCornellStride = 8;     // float4 per triangle: 6 of precomputed terms + bounding sphere + plane
-constexpr int kCornellF4    = 32 * kCornellStride;
+constexpr int kCornellPairs = 16;                      // triangles 2k, 2k+1 are one quad of CornellBox.hs: one plane test for both
+constexpr int kCornellF4    = 32 * kCornellStride + kCornellPairs;   // + one supporting plane per pair
 
 enum CounterSlot { C_SAMPLES = 0, C_IN_SPHERE, C_HITS, C_MARCH_DE, C_SHADE_DE, C_ITERS, C_NSLOTS = 8 };
 
