@@ -40,3 +40,10 @@ cudaError_t launch_march_fast(const MarchParams &p, int grid, cudaStream_t s) { 
 int march_fast_ctas_per_sm(int scene, int flags) { return march_ctas_per_sm_impl<MathFast>(scene, flags); }
 
 }  // namespace rmdf
+
+#if RMDF_DEBUG_TAIL
+extern "C" int rmdf_debug_tail(unsigned long long *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, rmdf::g_dbg_tail, sizeof(unsigned long long) * (size_t)n);
+}
+#endif

@@ -273,19 +273,14 @@ extern "C" int rmdf_envmap_convolve(rmdf_ctx *ctx, const float *rgb, int w, int 
     DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
     if ((rc = convolve_check(rgb, w, h, powers, np, out))) return rc;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    float *d_src = nullptr, *d_dst = nullptr;
+    // source and np results in the context's grow-only staging buffer (a cudaMalloc/cudaFree pair per call cost more than the sweep)
     const size_t nsrc = sizeof(float) * 3 * (size_t)w * h;
-    CU(cudaMalloc(&d_src, nsrc));
-    cudaError_t e = cudaMalloc(&d_dst, nsrc * np);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, rgb, nsrc, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        rc = rmdf_envmap_convolve_device(ctx, d_src, w, h, powers, np, d_dst);
-        if (rc == RMDF_OK) e = cudaMemcpyAsync(out, d_dst, nsrc * np, cudaMemcpyDeviceToHost, ctx->stream);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_src); if (d_dst) cudaFree(d_dst);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "rmdf_envmap_convolve: %s", cudaGetErrorString(e));
+    if ((rc = ensure_staging(ctx, nsrc * (size_t)(np + 1)))) return rc;
+    float *d_src = (float *)ctx->d_out, *d_dst = d_src + 3 * (size_t)w * h;
+    CU(cudaMemcpyAsync(d_src, rgb, nsrc, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = rmdf_envmap_convolve_device(ctx, d_src, w, h, powers, np, d_dst))) return rc;
+    CU(cudaMemcpyAsync(out, d_dst, nsrc * np, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return RMDF_OK;
 }
 
@@ -773,6 +768,10 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
         const int min_h = q > 4 ? q : 4, min_w = q > 8 ? q : 8;
         mp.item_h = 8 > min_h ? 8 : min_h; mp.item_w = kBlockDim;
         auto items = [&]() { return (int64_t)((wl.tile_w + mp.item_w - 1) / mp.item_w) * ((wl.tile_h + mp.item_h - 1) / mp.item_h) * wl.n_tiles; };
+        // 32×8 -> 32×4 already below 100 items per warp: the two cost the same per sample (16.70 / 16.74 ms), but the kernel's
+        // idle end is one worst-case item long — 8 tiles walked by one warp, ~0.3 ms (per-warp end times, profiles/dbg_tail.py:
+        // mean idle 0.23 ms with 32×8, 0.11 ms with 32×4) — which weighs 2×, 4× as much on a half, a quarter of the frame
+        if (mp.item_h > min_h && mp.item_h == 8 && items() < (int64_t)resident_warps * 100) mp.item_h >>= 1;
         while (items() < (int64_t)resident_warps * 24) {
             if (mp.item_h > min_h) mp.item_h >>= 1;
             else if (mp.item_w > min_w) mp.item_w >>= 1;
