@@ -476,6 +476,20 @@ def run_ours(args):
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     frame_cnt = dict(zip(("samples", "in_sphere", "hits", "march_de", "shade_de", "inner_iters"), cnt.tolist()))
     kernel_ms = float(kt.item())
+    # the same frame with the work order off (items claimed in scan order, as the first frame of a sequence always is):
+    # every timed step above ran in the order made from the step before it (rmdf_set_work_order, frame_sync.cuh)
+    sr.setWorkOrder(False)
+    sms = []
+    for _ in range(3):
+        flush.zero_(); barrier()
+        step_resident(); torch.cuda.synchronize()
+        sms.append(sr.counters()["last_kernel_ms"])
+    barrier()
+    sr.setWorkOrder(True)
+    st_ = torch.tensor([float(np.mean(sms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(st_, op=dist.ReduceOp.MAX)
+    scan_order_kernel_ms = float(st_.item())
     fp32_peak = sr.measureFp32Peak() if rank == 0 else None
     other = None
     if world == 1 and use_fast:                      # the bit-exact build on the same frame, for the record
@@ -523,6 +537,10 @@ def run_ours(args):
                          "algorithmic_flop_per_frame": flops, "kernel_ms": kernel_ms,
                          "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src}},
+            "work_order": {"enabled": True, "kernel_ms": kernel_ms, "scan_order_kernel_ms": scan_order_kernel_ms,
+                           "note": "every step claims its work items most-expensive-first, in the order a small kernel made from the previous "
+                                   "step's measured item costs (scheduling only: same pixels, same counters); kernel_ms includes that kernel; "
+                                   "scan_order_kernel_ms = the same frame with the order switched off, as a first frame is rendered"},
             "clocks": clocks,
         }
         if sharded:

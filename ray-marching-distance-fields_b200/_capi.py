@@ -25,7 +25,7 @@ EXPORTS = [
     "rmdf_envmap_resize_height", "rmdf_envmap_resize", "rmdf_envmap_convolve", "rmdf_envmap_convolve_device", "rmdf_envmap_convolve_rows_device",
     "rmdf_rgbe_roundtrip", "rmdf_envmap_bind", "rmdf_envmap_bind_cube", "rmdf_envmap_bind_cubes", "rmdf_envmap_get_cube", "rmdf_envmap_unbind",
     "rmdf_set_cornell", "rmdf_cornell_box_vertices", "rmdf_render_output_pixels", "rmdf_render", "rmdf_render_device",
-    "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_measure_fp32_peak", "rmdf_measure_mufu_peak",
+    "rmdf_julia", "rmdf_julia_device", "rmdf_julia_bands_device", "rmdf_mip_resolve_device", "rmdf_counters_get", "rmdf_counters_reset", "rmdf_set_work_order", "rmdf_measure_fp32_peak", "rmdf_measure_mufu_peak",
     "rmdf_shared_alloc", "rmdf_shared_free", "rmdf_shared_open", "rmdf_shared_close", "rmdf_enable_peer",
     "rmdf_host_register", "rmdf_host_unregister",
     "rmdf_frame_begin", "rmdf_frame_end", "rmdf_frame_sync_status",
@@ -103,6 +103,7 @@ def load(build_if_missing: bool = True):
     L.rmdf_mip_resolve_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rmdf_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.rmdf_counters_reset.argtypes = [vp]
+    L.rmdf_set_work_order.argtypes = [vp, C.c_int]
     L.rmdf_measure_fp32_peak.argtypes = [vp, fp, fp]
     L.rmdf_measure_mufu_peak.argtypes = [vp, fp]
     L.rmdf_shared_alloc.argtypes = [vp, C.c_int64, C.POINTER(vp), C.c_char_p]

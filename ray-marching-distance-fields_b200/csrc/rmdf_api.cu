@@ -58,6 +58,16 @@ struct rmdf_ctx {
     unsigned int sync_seq = 0;
     unsigned long long *d_counters = nullptr;
     uint64_t launches = 0;
+    // work order (frame_sync.cuh): item costs of the last frame, and the permutation made from them, valid for the
+    // next frame with the same work list (order_key)
+    int order_mode = 1;                // rmdf_set_work_order: 0 off, 1 on
+    unsigned int *d_order = nullptr, *d_rec = nullptr;
+    unsigned int *d_order_sync = nullptr;   // an ordered frame's queue word [0], CTA-exit counter [1] and, from kOrderSyncHeader on, its count matrix
+    size_t order_cap = 0;              // items d_order / d_rec hold
+    int order_n = 0;                   // items of the last recorded frame
+    bool order_sync_clean = false;     // d_order_sync is all zero (order_place_kernel leaves it so)
+    int order_key[24] = {0};
+    bool order_valid = false;          // d_order is a permutation for order_key
     EnvSlot env[RMDF_ENV_SLOTS];
     float4 *d_cornell = nullptr;
     bool have_cornell = false;
@@ -191,6 +201,9 @@ extern "C" void rmdf_destroy(rmdf_ctx *ctx)
     if (ctx->d_cornell) cudaFree(ctx->d_cornell);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
+    if (ctx->d_order) cudaFree(ctx->d_order);
+    if (ctx->d_rec) cudaFree(ctx->d_rec);
+    if (ctx->d_order_sync) cudaFree(ctx->d_order_sync);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -655,6 +668,105 @@ static int build_worklist(const rmdf_params *p, WorkList *wl)
     return RMDF_OK;
 }
 
+// ---- work order (frame_sync.cuh) --------------------------------------------------------------------------------
+// order_attach: point the frame's FrameSync at the cost record (always, when the work list qualifies) and at the
+// permutation of the previous frame (when that frame had the same work list); order_finish: after the frame's
+// kernel, turn its record into the permutation for the next frame.
+static int order_min_items()
+{
+    static const int v = [] { const char *e = getenv("RMDF_ORDER_MIN_ITEMS"); return e ? atoi(e) : 4096; }();
+    return v;
+}
+static bool order_attach(rmdf_ctx *ctx, const int key[24], int n_items, FrameSync *fs)
+{
+    fs->order = nullptr; fs->rec = nullptr; fs->counts = nullptr;
+    if (!ctx->order_mode || fs->queue_sys || fs->batch_max > 1u || n_items < order_min_items()) return false;
+    if (ctx->order_cap < (size_t)n_items) {
+        // cudaFree waits for the device: no frame that still uses the old buffers is in flight afterwards
+        if (ctx->d_order) { cudaFree(ctx->d_order); ctx->d_order = nullptr; }
+        if (ctx->d_rec) { cudaFree(ctx->d_rec); ctx->d_rec = nullptr; }
+        if (ctx->d_order_sync) { cudaFree(ctx->d_order_sync); ctx->d_order_sync = nullptr; }
+        ctx->order_cap = 0; ctx->order_valid = false;
+        const size_t chunks = ((size_t)n_items + kOrderChunk - 1) / kOrderChunk;
+        if (cudaMalloc(&ctx->d_order, (size_t)n_items * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&ctx->d_rec, (size_t)n_items * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc(&ctx->d_order_sync, (kOrderSyncHeader + chunks * kOrderBuckets) * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();                              // no memory for hints: render in scan order
+            if (ctx->d_order) { cudaFree(ctx->d_order); ctx->d_order = nullptr; }
+            if (ctx->d_rec) { cudaFree(ctx->d_rec); ctx->d_rec = nullptr; }
+            return false;
+        }
+        ctx->order_cap = (size_t)n_items;
+        ctx->order_sync_clean = false;
+    }
+    if (memcmp(key, ctx->order_key, sizeof ctx->order_key) != 0) {
+        memcpy(ctx->order_key, key, sizeof ctx->order_key);
+        ctx->order_valid = false;
+    }
+    // an ordered frame has its queue word, its CTA-exit counter and its count matrix in ONE buffer: one memset clears them
+    if (fs->queue == ctx->d_queue) fs->queue = ctx->d_order_sync;
+    fs->done = ctx->d_order_sync + 1;
+    fs->order = ctx->order_valid ? ctx->d_order : nullptr;
+    fs->rec = ctx->d_rec;
+    fs->counts = ctx->d_order_sync + kOrderSyncHeader;
+    return true;
+}
+// Clears what the frame's kernel counts in: the queue word and the CTA-exit counter and, for an ordered frame, its count
+// matrix — which the previous ordered frame's order_place_kernel has normally already done (order_sync_clean).
+static cudaError_t clear_frame_sync(rmdf_ctx *ctx, const FrameSync &fs)
+{
+    if (fs.counts == nullptr) return cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream);
+    if (ctx->order_sync_clean) return cudaSuccess;
+    const size_t chunks = (ctx->order_cap + kOrderChunk - 1) / kOrderChunk;
+    return cudaMemsetAsync(ctx->d_order_sync, 0, (kOrderSyncHeader + chunks * kOrderBuckets) * sizeof(unsigned int), ctx->stream);
+}
+static int order_finish(rmdf_ctx *ctx, const FrameSync &fs, int n_items)
+{
+    ctx->order_n = n_items;
+    ctx->order_sync_clean = false;
+    if (getenv("RMDF_ORDER_DEBUG")) return RMDF_OK;         // experiments: the host sorts (rmdf_debug_order_*)
+    cudaError_t e = launch_order_place(fs.rec, (unsigned)n_items, ctx->d_order_sync, ctx->d_order, ctx->stream);
+    if (e != cudaSuccess) { ctx->order_valid = false; return fail(RMDF_ERR_CUDA, "work-order kernel launch: %s", cudaGetErrorString(e)); }
+    ctx->order_valid = true;
+    ctx->order_sync_clean = true;                           // its last CTA zeroes the control buffer
+    ctx->launches++;
+    return RMDF_OK;
+}
+// experiments only (profiles/exp_order.py): the cost record of the last frame / a permutation for the next one
+extern "C" int rmdf_debug_order_get(rmdf_ctx *ctx, unsigned int *rec_host, int cap)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!ctx->d_rec || ctx->order_n <= 0 || cap < ctx->order_n) return -1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(rec_host, ctx->d_rec, (size_t)ctx->order_n * 4, cudaMemcpyDeviceToHost));
+    return ctx->order_n;
+}
+extern "C" int rmdf_debug_order_get_order(rmdf_ctx *ctx, unsigned int *order_host, int cap)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!ctx->d_order || !ctx->order_valid || ctx->order_n <= 0 || cap < ctx->order_n) return -1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(order_host, ctx->d_order, (size_t)ctx->order_n * 4, cudaMemcpyDeviceToHost));
+    return ctx->order_n;
+}
+extern "C" int rmdf_debug_order_set(rmdf_ctx *ctx, const unsigned int *order_host, int n)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    if (!ctx->d_order || n != ctx->order_n) return -1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(ctx->d_order, order_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+    ctx->order_valid = true;
+    return 0;
+}
+extern "C" int rmdf_set_work_order(rmdf_ctx *ctx, int enabled)
+{
+    DeviceGuard guard__; int rc = guard__.enter(ctx); if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    ctx->order_mode = enabled ? 1 : 0;
+    ctx->order_valid = false;
+    return RMDF_OK;
+}
+
 extern "C" int64_t rmdf_render_output_pixels(const rmdf_params *p, int32_t *n_tiles)
 {
     WorkList wl;
@@ -789,6 +901,10 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     }
     mp.blocks_x = bx;
     mp.blocks_y = (wl.tile_h + mp.item_h - 1) / mp.item_h;
+    // reciprocal for decode_item: q = (n·inv) >> 40 with inv = floor(2^40/d) + 1 equals floor(n/d) while n·d < 2^40
+    // (error n·(inv − 2^40/d)/2^40 <= n/2^40 < 1/d); n < blocks_x·blocks_y
+    mp.blocks_x_inv = (mp.blocks_x > 0 && (unsigned long long)mp.blocks_x * mp.blocks_y * (unsigned long long)mp.blocks_x < (1ull << 40))
+                    ? ((1ull << 40) / (unsigned long long)mp.blocks_x + 1ull) : 0ull;
     const int64_t n_items = (int64_t)mp.blocks_x * mp.blocks_y * wl.n_tiles;
     if (n_items > 0x7fffffff) return fail(RMDF_ERR_UNSUPPORTED, "frame too large: %lld work items", (long long)n_items);
     mp.n_items = (int)n_items;
@@ -809,9 +925,30 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
         if (v >= 1 && v <= 64) { mp.sync.batch_max = (unsigned)v; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
     }
     if (mp.n_items == 0 && mp.sync.signal == nullptr) return RMDF_OK;
+    const int okey[24] = { 1, p->scene, p->fb_w, p->fb_h, wl.rect_mode, wl.tile_x0, wl.tile_y0, wl.tile_w, wl.tile_h, wl.n_tiles,
+                           p->shard_count, p->shard_rank, wl.shard_skew, wl.shard_ty0, mp.item_w, mp.item_h, mp.n_items,
+                           (int)mp.sync.item_stride, (int)mp.sync.item_offset, (int)mp.sync.item_group, p->resolve_log2, p->flags, 0, 0 };
+    // work order: the fractals have the heavy-tailed item costs it pays for (measured: config 4 −0.35 %, one GPU's eighth of it
+    // −2.5 %, general power −5 %, config 1 −1…4 %); the Cornell box gains nothing and the CSG scene loses the 10 µs it costs
+    static const bool order_all = getenv("RMDF_ORDER_ALL") != nullptr;
+    const bool ordered = (p->scene == RMDF_SCENE_MB_POWER8 || p->scene == RMDF_SCENE_MB_GENERAL || order_all) &&
+                         order_attach(ctx, okey, mp.n_items, &mp.sync);
+    if (!ordered) { mp.sync.order = nullptr; mp.sync.rec = nullptr; mp.sync.counts = nullptr; }
     int grid = ctas_per_sm * ctx->sm_count;
+    // A frame of very few items is bound by the latency of its slowest one (config 1: one 8×4 tile marches for 80 of the
+    // frame's 90 µs), and that item runs faster with fewer warps on its scheduler: at least four items per warp
+    // (config 1: 8 → 3 CTAs per SM, 0.091 → 0.078 ms fast, 0.217 → 0.204 ms parity)
+    {
+        const int cap = (mp.n_items / 4 + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (grid > cap && !getenv("RMDF_NO_GRID_CAP")) grid = cap > ctx->sm_count ? cap : (grid < ctx->sm_count ? grid : ctx->sm_count);
+    }
+    if (const char *e = getenv("RMDF_GRID_CTAS_PER_SM")) {   // tuning override (experiments only)
+        const int v = atoi(e);
+        if (v >= 1 && v < ctas_per_sm) grid = v * ctx->sm_count;
+    }
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need > 0 ? need : 1;             // a rank without items still publishes its arrival flag
+    mp.sync.first_wave = (mp.sync.queue_sys || mp.sync.batch_max > 1u || getenv("RMDF_NO_FIRST_WAVE")) ? 0u : (unsigned)(grid * kWarpsPerCta);
 
     if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go" (see rmdf_frame_begin)
         cudaError_t ew = launch_wait_flags(go_word, 1, mp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
@@ -819,14 +956,15 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
         if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
         ctx->launches++;
     }
-    CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
+    CU(clear_frame_sync(ctx, mp.sync));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = (p->mode == RMDF_MODE_FAST) ? launch_march_fast(mp, grid, ctx->stream)
                                                 : launch_march_parity(mp, grid, ctx->stream);
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "march kernel launch: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    if (ordered && (rc = order_finish(ctx, mp.sync, mp.n_items))) return rc;   // inside the timed span: it is part of the frame's cost
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches++;
     return RMDF_OK;
 }
 
@@ -949,22 +1087,29 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
         ctx->sync_ctrl = nullptr;
     }
     if (jp.n_items == 0 && jp.sync.signal == nullptr) return RMDF_OK;
+    const int okey[24] = { 2, jp.w, jp.h, jp.y0, jp.y1, jp.resolve_log2, jp.frame_layout, jp.band_h, jp.shard_rank, jp.shard_count,
+                           jp.item_h, jp.blocks_x, jp.blocks_y, jp.n_items, (int)jp.sync.item_stride, (int)jp.sync.item_offset,
+                           (int)jp.sync.item_group, 0, 0, 0, 0, 0, 0, 0 };
+    const bool ordered = (getenv("RMDF_ORDER_JULIA") != nullptr) && order_attach(ctx, okey, jp.n_items, &jp.sync);
+    if (!ordered) { jp.sync.order = nullptr; jp.sync.rec = nullptr; jp.sync.counts = nullptr; }
     int grid = julia_ctas_per_sm() * ctx->sm_count;
     const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need > 0 ? need : 1;
+    jp.sync.first_wave = (jp.sync.queue_sys || jp.sync.batch_max > 1u || getenv("RMDF_NO_FIRST_WAVE")) ? 0u : (unsigned)(grid * kWarpsPerCta);
     if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go"
         cudaError_t ew = launch_wait_flags(go_word, 1, jp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
                                            ctx->d_queue + 2, ctx->stream);
         if (ew != cudaSuccess) return fail(RMDF_ERR_CUDA, "frame wait launch: %s", cudaGetErrorString(ew));
         ctx->launches++;
     }
-    CU(cudaMemsetAsync(ctx->d_queue, 0, 2 * sizeof(unsigned int), ctx->stream));
+    CU(clear_frame_sync(ctx, jp.sync));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     cudaError_t e = launch_julia(jp, grid, ctx->stream);
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "julia kernel launch: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    if (ordered) { int rc = order_finish(ctx, jp.sync, jp.n_items); if (rc) return rc; }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches++;
     return RMDF_OK;
 }
 

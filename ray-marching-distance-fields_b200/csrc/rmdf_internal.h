@@ -41,6 +41,7 @@ struct MarchParams {
     int   item_h;                     // rows per work item: 4, 8, 16 or 32
     int   item_w;                     // columns per work item: 32, or 16 / 8 on frames too small to fill the machine
     int   blocks_x, blocks_y;         // 32×item_h blocks per rect
+    unsigned long long blocks_x_inv;  // floor(2^40 / blocks_x) + 1 when that divides every in-rect index exactly, else 0 (decode_item)
     int   n_items;
     int   out_stride;                 // output row stride in pixels (already >> resolve_log2)
     // resources
@@ -85,6 +86,7 @@ cudaError_t measure_mufu_peak(int sm_count, cudaStream_t s, float *gops);
 cudaError_t preload_frame_sync_kernels();
 cudaError_t launch_frame_begin(unsigned int *ctrl, unsigned int seq, cudaStream_t s);
 cudaError_t launch_wait_flags(const unsigned int *flags, int n, unsigned int value, unsigned int timeout_ms, unsigned int *status, cudaStream_t s);
+cudaError_t launch_order_place(const unsigned int *rec, unsigned int n_items, unsigned int *sync, unsigned int *order, cudaStream_t s);
 cudaError_t launch_mip_resolve(const uint32_t *in_dev, int w, int h, int levels, uint32_t *out_dev, cudaStream_t s);
 
 }  // namespace rmdf

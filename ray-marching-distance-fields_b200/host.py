@@ -226,6 +226,10 @@ class ShaderRenderer:
     def sync(self):
         check(self._lib.rmdf_sync(self._h))
 
+    def setWorkOrder(self, enabled: bool):
+        """rmdf_set_work_order: claim work items most-expensive-first, from the previous frame's item costs (scheduling only)."""
+        check(self._lib.rmdf_set_work_order(self._h, 1 if enabled else 0))
+
     # -- HDREnvMap.hs ---------------------------------------------------------------
     def resizeHDRImage(self, img, dstw: int) -> np.ndarray:
         img = _as_f32(img)

@@ -268,3 +268,63 @@ def test_error_message_through_the_context_from_another_thread(sr, R):
     # the caller's current device is what it was (DeviceGuard)
     import torch
     assert torch.cuda.current_device() == 0
+
+
+def test_work_order_never_changes_a_frame(sr, R, oracle_envs):
+    """rmdf_set_work_order (frame_sync.cuh "work order"): from the second frame of a sequence on, the kernel claims
+    its items most-expensive-first from the previous frame's measured costs.  Pure scheduling — every frame of the
+    sequence, with other work lists (another size, a tile, a moved camera) in between, equals the scan-order frame
+    word for word, and every sample is rendered exactly once (counters)."""
+    import torch
+    for s in range(5):
+        sr.bindCubeMap(s, oracle_envs[s])
+    w, h = 2048, 1536
+    out = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+
+    def frame(scene, t, mode, ww=w, hh=h, **kw):
+        out.zero_()
+        sr.resetCounters()
+        sr.renderDevice(sr.makeParams(scene, None, ww, hh, t, mode=mode, **kw), out.data_ptr())
+        sr.sync()
+        c = sr.counters()
+        return out[: (ww >> kw.get("resolve_log2", 0)) * (hh >> kw.get("resolve_log2", 0))].cpu().numpy().copy(), \
+            {k: c[k] for k in ("samples", "in_sphere", "hits", "march_de", "shade_de", "inner_iters")}
+
+    L = sr._lib
+    L.rmdf_debug_order_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.rmdf_debug_order_get_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+
+    def check_order():
+        """the permutation the device made = a stable sort of the recorded costs by octave, most expensive first"""
+        rec, order = np.zeros(1 << 20, np.uint32), np.zeros(1 << 20, np.uint32)
+        n = L.rmdf_debug_order_get(sr.handle, rec.ctypes.data, rec.size)
+        assert n > 0 and L.rmdf_debug_order_get_order(sr.handle, order.ctypes.data, order.size) == n
+        lg = np.floor(np.log2(np.maximum(rec[:n], 1).astype(np.float64))).astype(np.int64)
+        assert np.array_equal(order[:n], np.argsort(-lg, kind="stable").astype(np.uint32))
+        return n
+
+    for scene, mode in ((2, R.MODE_PARITY), (2, R.MODE_FAST), (3, R.MODE_FAST)):
+        sr.setWorkOrder(False)
+        ref0, cnt0 = frame(scene, 0.0, mode)
+        ref1, cnt1 = frame(scene, 0.7, mode)
+        refk, cntk = frame(scene, 0.0, mode, resolve_log2=2)
+        sr.setWorkOrder(True)
+        launches = sr.counters()["launches"]
+        for i in range(3):                                   # frame 0 records, frames 1 and 2 run in cost order
+            got, cnt = frame(scene, 0.0, mode)
+            assert np.array_equal(got, ref0) and cnt == cnt0, (scene, mode, i)
+            assert check_order() >= 4096
+        assert sr.counters()["launches"] == launches + 6     # each frame: the march kernel + the order kernel
+        got, cnt = frame(scene, 0.7, mode)                   # the camera moved: last frame's order, still every item once
+        assert np.array_equal(got, ref1) and cnt == cnt1
+        got, cnt = frame(scene, 0.0, mode, 520, 500)         # another work list in between (ragged edges)
+        check_order()
+        got, cnt = frame(scene, 0.0, mode, resolve_log2=2)   # and another one: starts over in scan order
+        assert np.array_equal(got, refk) and cnt == cntk
+        got, cnt = frame(scene, 0.0, mode, resolve_log2=2)
+        assert np.array_equal(got, refk) and cnt == cntk
+        got, cnt = frame(scene, 0.0, mode)
+        assert np.array_equal(got, ref0) and cnt == cnt0
+    launches = sr.counters()["launches"]
+    frame(0, 0.0, R.MODE_FAST); frame(1, 0.0, R.MODE_FAST)
+    assert sr.counters()["launches"] == launches + 2         # Cornell and CSG frames are not ordered (nothing to gain)
