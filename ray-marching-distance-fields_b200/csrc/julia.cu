@@ -55,23 +55,48 @@ __device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2
     return w;
 }
 
-// One orbit step for both slots (go, Fractal2D.hs:85-90): the escape test comes first; `it` is the
-// iteration number recorded for a slot that escapes here.  A slot that has escaped is frozen by
-// poisoning its additive constant with NaN: its orbit is NaN from the next update on and `|z|² > 16`
-// stays false for it, so the common path costs one max + one compare for both slots.
-#define RMDF_JULIA_STEP(it)                                                                       \
+// Two orbit steps for both slots (go, Fractal2D.hs:85-90), with ONE escape test.  The reference tests |z|² > 16 before
+// every update; here the test before the first update of a pair is skipped and made up for at the second: an orbit
+// that has left the disc of radius 4 never comes back (|z² + c| >= |z|² − |c| > 4 for |c| < 2, and |c| <= 1.4 here),
+// so it is still outside one step later — then the skipped test's |z|² (its operands are still in registers) says in
+// which of the two iterations it left.  Nothing overflows before the test fires: |z| <= 4 at the last test that passed
+// (or z is the start value, a coordinate of at most a few 10^5), so two updates stay finite.  A slot that has
+// escaped is frozen by poisoning its additive constant with NaN: its orbit is NaN from the next update on and
+// `|z|² > 16` stays false for it, so the common path costs one max + one compare for both slots per pair.
+//
+// Roundings are the reference's, operation by operation (Data.Complex: (zr·zr − zi·zi) + cr, (zr·zi + zi·zr) + ci):
+//   2·p + ji as ONE packed FMA: p + p = 2p exactly, so RN(2p + ji) = RN((p + p) + ji);
+//   zr² − zi² of the untested step as fma(zi², −1, zr²): exact product, so it is RN(zr² − zi²) — written this way because
+//   ptxas contracts a packed product whose only use is a sum INTO that sum (packed_f32.cuh), which would round zr·zr − zi²
+//   once instead of twice; as the addend of an explicit FMA there is nothing to contract.  Where both squares have a second
+//   use (the tested step's |z|²) the plain difference is safe.  tests/test_host_cpu.py checks every FFMA2 of this unit
+//   for its literal −1 / 2 multiplier.
+#define RMDF_JULIA_UPDATE(diff)                                                                   \
     {                                                                                             \
-        const f2 m = zr2 + zi2;                                                                   \
-        if (fmaxf(m.x, m.y) > 4.0f * 4.0f) {                                                      \
-            if (m.x > 16.0f) { it0 = (it); m0 = m.x; done |= 1u; jr.x = kNaN; }                   \
-            if (m.y > 16.0f) { it1 = (it); m1 = m.y; done |= 2u; jr.y = kNaN; }                   \
-            if (done == 3u) goto finished;                                                        \
-        }                                                                                         \
-        const f2 nr = (zr2 - zi2) + jr;                                                           \
+        const f2 nr = (diff) + jr;                                                                \
         const f2 p = zr * zi;                                                                     \
-        const f2 ni = (p + p) + ji;                                                               \
+        const f2 ni = fma2(2.0f, p, ji);                                                          \
         zr = nr; zi = ni;                                                                         \
         zr2 = zr * zr; zi2 = zi * zi;                                                             \
+    }
+#define RMDF_JULIA_PAIR(it)                                                                       \
+    {                                                                                             \
+        const f2 pr2 = zr2, pi2 = zi2;                               /* squares of z(it) */        \
+        RMDF_JULIA_UPDATE(fma2(-1.0f, pi2, pr2))                                                  \
+        const f2 m = zr2 + zi2;                                      /* |z(it + 1)|² */            \
+        if (fmaxf(m.x, m.y) > 4.0f * 4.0f) {                                                      \
+            const f2 m_prev = pr2 + pi2;                             /* the skipped test */        \
+            if (m.x > 16.0f) {                                                                    \
+                if (m_prev.x > 16.0f) { it0 = (it); m0 = m_prev.x; } else { it0 = (it) + 1; m0 = m.x; } \
+                done |= 1u; jr.x = kNaN;                                                          \
+            }                                                                                     \
+            if (m.y > 16.0f) {                                                                    \
+                if (m_prev.y > 16.0f) { it1 = (it); m1 = m_prev.y; } else { it1 = (it) + 1; m1 = m.y; } \
+                done |= 2u; jr.y = kNaN;                                                          \
+            }                                                                                     \
+            if (done == 3u) goto finished;                                                        \
+        }                                                                                         \
+        RMDF_JULIA_UPDATE(zr2 - zi2)                                                              \
     }
 // The reference's 1-cycle test (newZ == z ⇒ maxIter) is only a shortcut: a repeating orbit never escapes, so it
 // ends at maxIter with the same z either way.  Testing once per block of eight iterations for
@@ -88,10 +113,9 @@ __device__ __forceinline__ uint32_t julia_word(int iter, float mag2, float log_2
 #define RMDF_JULIA_BLOCK_LEN 8     // iterations between periodicity tests (a divisor of 40): 4 or 8
 #endif
 #if RMDF_JULIA_BLOCK_LEN == 8
-#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_STEP(b) RMDF_JULIA_STEP((b) + 1) RMDF_JULIA_STEP((b) + 2) RMDF_JULIA_STEP((b) + 3) \
-                            RMDF_JULIA_STEP((b) + 4) RMDF_JULIA_STEP((b) + 5) RMDF_JULIA_STEP((b) + 6) RMDF_JULIA_STEP((b) + 7)
+#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_PAIR(b) RMDF_JULIA_PAIR((b) + 2) RMDF_JULIA_PAIR((b) + 4) RMDF_JULIA_PAIR((b) + 6)
 #else
-#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_STEP(b) RMDF_JULIA_STEP((b) + 1) RMDF_JULIA_STEP((b) + 2) RMDF_JULIA_STEP((b) + 3)
+#define RMDF_JULIA_BLOCK(b) RMDF_JULIA_PAIR(b) RMDF_JULIA_PAIR((b) + 2)
 #endif
 
 // KD: the coordinate divisions col / w and row / h (Fractal2D.hs:81-82) as correctly rounded known-divisor
@@ -244,7 +268,8 @@ julia_kernel(const JuliaParams P)
     signal_when_grid_done(P.sync);
 }
 #undef RMDF_JULIA_BLOCK
-#undef RMDF_JULIA_STEP
+#undef RMDF_JULIA_PAIR
+#undef RMDF_JULIA_UPDATE
 #undef RMDF_JULIA_PERIODIC
 
 cudaError_t launch_julia(const JuliaParams &p, int grid, cudaStream_t s)

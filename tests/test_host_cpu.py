@@ -43,9 +43,9 @@ def test_library_exports_every_declared_symbol(R):
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure path")
 def test_ieee_units_have_no_packed_contraction(R):
     """The bit-exact units are compiled -fmad=false, but ptxas contracts the PACKED forms mul.rn.f32x2 +
-    add.rn.f32x2 into FFMA2 regardless (csrc/packed_f32.cuh).  Disassemble the built objects: the Julia and
-    parity-march units must hold no packed FMA, while the fast unit must hold them (its iteration is built on
-    FFMA2/FMUL2) — a check that the disassembly itself works."""
+    add.rn.f32x2 into FFMA2 regardless (csrc/packed_f32.cuh).  Disassemble the built objects: the parity-march unit
+    must hold no packed FMA, the Julia unit only its two intended exact ones, while the fast unit must hold them
+    (its iteration is built on FFMA2/FMUL2) — a check that the disassembly itself works."""
     import shutil
     R._capi.load(build_if_missing=True)
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
@@ -57,9 +57,15 @@ def test_ieee_units_have_no_packed_contraction(R):
         sass = subprocess.run([cuobjdump, "-sass", str(objdir / name)], capture_output=True, text=True, check=True).stdout
         return re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", sass, flags=re.M)
 
-    for unit in ("julia.cu.o", "march_parity.cu.o"):
-        o = ops(unit)
-        assert len(o) > 1000 and "FFMA2" not in o, "%s: ptxas contracted a packed multiply-add" % unit
+    o = ops("march_parity.cu.o")
+    assert len(o) > 1000 and "FFMA2" not in o, "march_parity.cu.o: ptxas contracted a packed multiply-add"
+    # julia.cu writes two EXACT packed FMAs on purpose — 2·p + ci and zi²·(−1) + zr² (csrc/julia.cu, RMDF_JULIA_PAIR) — whose
+    # multiplier is the literal 2 or −1; a contraction of a product into a sum would have two register multiplicands
+    sass = subprocess.run([cuobjdump, "-sass", str(objdir / "julia.cu.o")], capture_output=True, text=True, check=True).stdout
+    fma2 = [l for l in sass.splitlines() if re.search(r"\bFFMA2\b", l)]
+    assert len(fma2) >= 48
+    for l in fma2:
+        assert re.search(r"FFMA2\s+R\d+, R\d+(\.\w+)*, (2|-1), ", l), "julia.cu.o: ptxas contracted a packed multiply-add: " + l.strip()
     assert "FMUL2" in ops("julia.cu.o") and "FADD2" in ops("julia.cu.o")
     fast = ops("march_fast.cu.o")
     assert "FFMA2" in fast and "FMUL2" in fast
