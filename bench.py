@@ -471,8 +471,12 @@ def run_ours(args):
         kms.append(sr.counters()["last_kernel_ms"])       # this rank's march kernel alone (events around the launch)
     barrier()
     kt = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
+    rank_kernel_ms = None
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        per_rank = [torch.zeros_like(kt) for _ in range(world)]
+        dist.all_gather(per_rank, kt)
+        rank_kernel_ms = [round(float(t_.item()), 4) for t_ in per_rank]     # how even the deal is: each rank's own kernel
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
     frame_cnt = dict(zip(("samples", "in_sphere", "hits", "march_de", "shade_de", "inner_iters"), cnt.tolist()))
     kernel_ms = float(kt.item())
@@ -545,6 +549,7 @@ def run_ours(args):
         }
         if sharded:
             line["frame_equals_single_gpu"] = frame_same
+            line["rank_kernel_ms"] = rank_kernel_ms
             if julia_n is not None:
                 line["julia_8k_64spp"] = julia_n
         if tol is not None:

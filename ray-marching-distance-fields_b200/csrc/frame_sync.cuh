@@ -38,6 +38,7 @@ struct FrameSync {
     unsigned int  item_stride;         // interleaved deal, in groups of item_group x-adjacent items: local item j = (q, m) with
     unsigned int  item_offset;         // q = j / item_group, m = j mod item_group is frame item (q·item_stride + item_offset)·
     unsigned int  item_group;          // item_group + m.  A group covers >= 128 B of every output row, so that no 64 B line of
+    unsigned int  item_rotate;         // 1: the rank's slot inside each window of item_stride groups rotates with the window (frame_item)
     unsigned int  items_total;         // a HOST frame buffer is shared by two GPUs (partial-line writes over PCIe: the end-to-
                                        // end frame took 4.2 instead of 2.7 ms at N = 8 with single-item interleaving)
     // cost-ordered queue (see "work order" below); both nullptr = items in their natural order, nothing recorded
@@ -86,7 +87,13 @@ __device__ __forceinline__ unsigned frame_item(const FrameSync &S, unsigned j)
 {
     if (S.item_stride == 1u) return j;
     const unsigned q = j / S.item_group, m = j - q * S.item_group;
-    return (q * S.item_stride + S.item_offset) * S.item_group + m;
+    // window q = the groups q·world … q·world + world − 1, one for every rank: this rank's slot in it rotates with a hash
+    // of q (item_rotate).  With a fixed slot a rank owns the same columns of every item row — vertical stripes, and the
+    // ranks' kernels differed by 6 % at N = 8 (2.04 … 2.16 ms) — rotated, every rank samples every column
+    const unsigned rot = S.item_rotate ? ((q * 2654435761u) >> 16) % S.item_stride : 0u;
+    unsigned slot = S.item_offset + rot;
+    if (slot >= S.item_stride) slot -= S.item_stride;
+    return (q * S.item_stride + slot) * S.item_group + m;
 }
 
 // The warp's current batch of work items [next, end) — all members are warp-uniform.
