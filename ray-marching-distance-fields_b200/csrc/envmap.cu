@@ -352,19 +352,24 @@ cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int f
     return cudaGetLastError();
 }
 
-// float RGB faces → half4 texels (CUDA has no 3-channel half format); also rounds to half
-__global__ void pack_half4_kernel(float *__restrict__ faces, int n, ushort4 *__restrict__ out)
+// float RGB faces → half4 texels (CUDA has no 3-channel half format), written straight into the slot's two arrays (layered
+// for the parity path's exact fetches, cube map for the fast path's hardware filtering) through their surface objects;
+// also rounds the float faces to half in place (rmdf_envmap_get_cube returns what the textures hold)
+__global__ void pack_half4_kernel(float *__restrict__ faces, int fw, cudaSurfaceObject_t layered, cudaSurfaceObject_t cube)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, face = blockIdx.z;
+    if (x >= fw) return;
+    const size_t i = ((size_t)face * fw + y) * fw + x;
     const __half r = __float2half_rn(faces[i * 3]), g = __float2half_rn(faces[i * 3 + 1]), b = __float2half_rn(faces[i * 3 + 2]);
     faces[i * 3] = __half2float(r); faces[i * 3 + 1] = __half2float(g); faces[i * 3 + 2] = __half2float(b);
-    out[i] = make_ushort4(__half_as_ushort(r), __half_as_ushort(g), __half_as_ushort(b), 0x3c00 /* 1.0 */);
+    const ushort4 t = make_ushort4(__half_as_ushort(r), __half_as_ushort(g), __half_as_ushort(b), 0x3c00 /* 1.0 */);
+    surf2DLayeredwrite(t, layered, x * (int)sizeof(ushort4), y, face);
+    surf2DLayeredwrite(t, cube, x * (int)sizeof(ushort4), y, face);       // a cube map array is a 6-layer surface, layer = face
 }
-cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s)
+cudaError_t launch_pack_half4(const float *faces_dev, int face_w, cudaSurfaceObject_t layered, cudaSurfaceObject_t cube, cudaStream_t s)
 {
-    const int n = 6 * face_w * face_w;
-    pack_half4_kernel<<<(n + 255) / 256, 256, 0, s>>>(const_cast<float *>(faces_dev), n, reinterpret_cast<ushort4 *>(half4_dev));
+    const dim3 grid((unsigned)(face_w + 127) / 128, (unsigned)face_w, 6);
+    pack_half4_kernel<<<grid, 128, 0, s>>>(const_cast<float *>(faces_dev), face_w, layered, cube);
     return cudaGetLastError();
 }
 

@@ -43,7 +43,7 @@ struct EnvSlot {
     cudaArray_t arr_layered = nullptr, arr_cube = nullptr;
     cudaTextureObject_t tex_point = 0, tex_cube = 0, tex_cube_nearest = 0;
     float *faces_dev = nullptr;        // 6·w·w·3 half-rounded floats (for rmdf_envmap_get_cube)
-    void *half4_dev = nullptr;         // 6·w·w half4 staging for the array copies
+    cudaSurfaceObject_t surf_layered = 0, surf_cube = 0;   // the two arrays as 2D layered surfaces: the pack kernel writes the texels
 };
 
 struct rmdf_ctx {
@@ -182,10 +182,11 @@ static void free_slot(EnvSlot &s)
     if (s.tex_point) cudaDestroyTextureObject(s.tex_point);
     if (s.tex_cube) cudaDestroyTextureObject(s.tex_cube);
     if (s.tex_cube_nearest) cudaDestroyTextureObject(s.tex_cube_nearest);
+    if (s.surf_layered) cudaDestroySurfaceObject(s.surf_layered);
+    if (s.surf_cube) cudaDestroySurfaceObject(s.surf_cube);
     if (s.arr_layered) cudaFreeArray(s.arr_layered);
     if (s.arr_cube) cudaFreeArray(s.arr_cube);
     if (s.faces_dev) cudaFree(s.faces_dev);
-    if (s.half4_dev) cudaFree(s.half4_dev);
     s = EnvSlot();
 }
 
@@ -325,25 +326,24 @@ extern "C" int rmdf_rgbe_roundtrip(float *rgb, int64_t npix)
 static int make_slot_textures(rmdf_ctx *ctx, EnvSlot &s, int fw, const float *faces_dev_src)
 {
     cudaStream_t st = ctx->stream;
-    const size_t ntex = (size_t)6 * fw * fw;
     const bool fresh = (s.arr_layered == nullptr);
     cudaError_t e = cudaSuccess;
-    if (!s.half4_dev) e = cudaMalloc(&s.half4_dev, ntex * 8);
-    if (e == cudaSuccess) e = launch_pack_half4(faces_dev_src, fw, s.half4_dev, st);
-    ctx->launches++;
     const cudaChannelFormatDesc desc = cudaCreateChannelDescHalf4();
     const cudaExtent ext = make_cudaExtent((size_t)fw, (size_t)fw, 6);
-    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_layered, &desc, ext, cudaArrayLayered);
-    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_cube, &desc, ext, cudaArrayCubemap);
-    for (int which = 0; which < 2 && e == cudaSuccess; which++) {
-        cudaMemcpy3DParms cp;
-        memset(&cp, 0, sizeof cp);
-        cp.srcPtr = make_cudaPitchedPtr(s.half4_dev, (size_t)fw * 8, (size_t)fw, (size_t)fw);
-        cp.dstArray = which ? s.arr_cube : s.arr_layered;
-        cp.extent = ext;
-        cp.kind = cudaMemcpyDeviceToDevice;
-        e = cudaMemcpy3DAsync(&cp, st);
+    // surface-writable arrays: ONE kernel rounds the faces to half and writes the texels of both arrays (a staging buffer
+    // and two cudaMemcpy3DAsync per map cost ~30 µs a map in the per-frame upload of the end-to-end path)
+    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_layered, &desc, ext, cudaArrayLayered | cudaArraySurfaceLoadStore);
+    if (fresh && e == cudaSuccess) e = cudaMalloc3DArray(&s.arr_cube, &desc, ext, cudaArrayCubemap | cudaArraySurfaceLoadStore);
+    if (fresh && e == cudaSuccess) {
+        cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = s.arr_layered;
+        e = cudaCreateSurfaceObject(&s.surf_layered, &rd);
+        rd.res.array.array = s.arr_cube;
+        if (e == cudaSuccess) e = cudaCreateSurfaceObject(&s.surf_cube, &rd);
     }
+    if (e == cudaSuccess) e = launch_pack_half4(faces_dev_src, fw, s.surf_layered, s.surf_cube, st);
+    ctx->launches++;
     if (fresh && e == cudaSuccess) {
         cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
         rd.resType = cudaResourceTypeArray;
@@ -934,7 +934,8 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     // work order: the fractals have the heavy-tailed item costs it pays for (measured: config 4 −0.35 %, one GPU's eighth of it
     // −2.5 %, general power −5 %, config 1 −1…4 %); the Cornell box gains nothing and the CSG scene loses the 10 µs it costs
     static const bool order_all = getenv("RMDF_ORDER_ALL") != nullptr;
-    const bool ordered = (p->scene == RMDF_SCENE_MB_POWER8 || p->scene == RMDF_SCENE_MB_GENERAL || order_all) &&
+    // (a frame drawn as the reference's 64 tiles cycles through 64 work lists: nothing to learn from the call before)
+    const bool ordered = (p->scene == RMDF_SCENE_MB_POWER8 || p->scene == RMDF_SCENE_MB_GENERAL || order_all) && wl.rect_mode != 1 &&
                          order_attach(ctx, okey, mp.n_items, &mp.sync);
     if (!ordered) { mp.sync.order = nullptr; mp.sync.rec = nullptr; mp.sync.counts = nullptr; }
     int grid = ctas_per_sm * ctx->sm_count;

@@ -80,7 +80,7 @@ cudaError_t launch_convolve(const float *src_dev, int w, int h, const float *pow
                             float *out_dev, int dst_y0, int dst_y1, cudaStream_t s);
 cudaError_t launch_resize(const float *src_dev, int w, int h, int dstw, int dsth, float *out_dev, cudaStream_t s);
 cudaError_t launch_latlong_to_cube(const float *latlong_dev, int w, int h, int face_w, float *faces_dev, cudaStream_t s);
-cudaError_t launch_pack_half4(const float *faces_dev, int face_w, void *half4_dev, cudaStream_t s);
+cudaError_t launch_pack_half4(const float *faces_dev, int face_w, cudaSurfaceObject_t layered, cudaSurfaceObject_t cube, cudaStream_t s);
 cudaError_t measure_fp32_peak(int sm_count, cudaStream_t s, float *tflops, float *sm_mhz);
 cudaError_t measure_mufu_peak(int sm_count, cudaStream_t s, float *gops);
 cudaError_t preload_frame_sync_kernels();
