@@ -47,4 +47,14 @@ with R.ShaderRenderer(0) as sr:
             sr.frameEnd(ptr + fb, 2, seq, 3000)
             assert sr.frameSyncStatus() == 0 and b.frameSyncStatus() == 0
         b.sync(); sr.sharedFree(ptr)
+    # round 2, third session: the cost-ordered queue (run with RMDF_ORDER_MIN_ITEMS=64 so that these small frames qualify):
+    # record + order_place_kernel + ordered claims, whole frames and one rank's share of a rotated two-rank deal
+    for mode in (0, 1):
+        pf = sr.makeParams(2, None, 256, 128, 1.0, mode=mode)
+        ptr, _ = sr.sharedAlloc(256 * 128 * 4 + 512)
+        for _ in range(3):
+            sr.renderDevice(pf, ptr)
+        for seq in (1, 2, 3):
+            sr.frameBegin(ptr + 256 * 128 * 4, 0, 2, seq, 3000, 0); sr.renderDevice(pf, ptr)
+        sr.sync(); sr.sharedFree(ptr)
     print("sanitize workload done", sr.counters()["launches"], "launches")

@@ -33,8 +33,6 @@ struct FrameSync {
     unsigned int *signal;              // arrival flag to publish when the last CTA has stored; nullptr = none
     unsigned int  signal_value;
     int           queue_sys;           // the queue is shared with other GPUs: claim with a system-scope atomic
-    unsigned int  batch_max;           // items per claim (1; > 1 only through the RMDF_BATCH_MAX tuning override: batches of
-    unsigned int  batch_div;           // min(batch_max, remaining / batch_div) consecutive items, see the note above)
     unsigned int  item_stride;         // interleaved deal, in groups of item_group x-adjacent items: local item j = (q, m) with
     unsigned int  item_offset;         // q = j / item_group, m = j mod item_group is frame item (q·item_stride + item_offset)·
     unsigned int  item_group;          // item_group + m.  A group covers >= 128 B of every output row, so that no 64 B line of
@@ -72,11 +70,17 @@ __device__ __forceinline__ unsigned ordered_item(const FrameSync &S, unsigned po
 {
     return S.order ? __ldg(S.order + pos) : pos;
 }
-// lane 0 notes what the finished item cost (t0 = item_clock() at the claim); class 0 = the most expensive octave
-__device__ __forceinline__ void record_item(const FrameSync &S, unsigned item, unsigned t0, int lane)
+// Lane 0 notes which item the warp has claimed and when — in two words of shared memory, not in registers: kept live across
+// the whole item they cost the march kernel's 64-register budget one instruction per Mandelbulb iteration (33 instead of 32
+// issue slots, +3 % on the frame) — and, when the item is finished, what it cost (class 0 = the most expensive octave).
+__device__ __forceinline__ void begin_item(const FrameSync &S, unsigned *slot, unsigned item, int lane)
+{
+    if (S.rec != nullptr && lane == 0) { slot[0] = item; slot[1] = item_clock(); }
+}
+__device__ __forceinline__ void record_item(const FrameSync &S, const unsigned *slot, int lane)
 {
     if (S.rec != nullptr && lane == 0) {
-        const unsigned cycles = item_clock() - t0;
+        const unsigned item = slot[0], cycles = item_clock() - slot[1];
         S.rec[item] = cycles;
         atomicAdd(S.counts + (item / kOrderChunk) * kOrderBuckets + __clz((int)(cycles | 1u)), 1u);
     }
@@ -96,34 +100,28 @@ __device__ __forceinline__ unsigned frame_item(const FrameSync &S, unsigned j)
     return (q * S.item_stride + slot) * S.item_group + m;
 }
 
-// The warp's current batch of work items [next, end) — all members are warp-uniform.
-struct ItemBatch { unsigned next = 0, end = 0, seen = 0; };
-
-// Next work item of this warp (an index into this context's own item list), or a value >= n_items when the queue is
-// drained.  Lane 0 claims a new batch when the current one is used up.
-__device__ __forceinline__ unsigned next_item(const FrameSync &S, ItemBatch &b, unsigned n_items, int lane)
+// The warp's first queue position, and its next ones (values >= the item count: the queue is drained).  The item loop is
+//     for (unsigned q = first_item(S, lane); q < n_items; q = claim_item(S, lane)) …
+// with ONE claim site and no state besides q: a stateful "next item" with a first-call test cost the Cornell kernel
+// eight registers (72 → 80: 7 → 6 resident CTAs, +4 %).
+// A warp's first item needs no claim: grid warp w takes queue position w, the queue word hands out first_wave + 0, 1, …
+// With a cost-ordered queue this also PLACES the frame's most expensive items: four per CTA, one per scheduler, CTA
+// after CTA over the SMs.  Claimed in arrival order they pile up on some SMs, where eight crevice warps then share one
+// scheduler (config 1: 0.111 ms claimed, 0.081 ms placed).
+__device__ __forceinline__ unsigned claim_item(const FrameSync &S, int lane)
 {
-    if (b.next == b.end) {
-        if (S.first_wave != 0u && b.end == 0u) {
-            // A warp's first item needs no claim: grid warp w takes queue position w, the queue word hands out
-            // first_wave + 0, 1, …  With a cost-ordered queue this also PLACES the frame's most expensive items: four per
-            // CTA, one per scheduler, CTA after CTA over the SMs.  Claimed in arrival order they pile up on some SMs,
-            // where eight crevice warps then share one scheduler (config 1: 0.111 ms claimed, 0.081 ms placed).
-            const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-            b.next = w; b.end = w + 1u; b.seen = w;
-            return b.next++;
-        }
-        unsigned n = 1u;
-        if (S.batch_max > 1u) {
-            const unsigned remaining = n_items > b.seen ? n_items - b.seen : 0u;
-            n = min(S.batch_max, max(1u, remaining / S.batch_div));
-        }
-        unsigned base = 0u;
-        if (lane == 0) base = S.queue_sys ? atomicAdd_system(S.queue, n) : atomicAdd(S.queue, n);
-        base = __shfl_sync(0xffffffffu, base, 0) + S.first_wave;
-        b.next = base; b.end = base + n; b.seen = base;
-    }
-    return b.next++;
+    unsigned base = 0u;
+    if (lane == 0) base = S.queue_sys ? atomicAdd_system(S.queue, 1u) : atomicAdd(S.queue, 1u);
+    return __shfl_sync(0xffffffffu, base, 0) + S.first_wave;
+}
+// PLACED = the kernel takes part in the work order (the Mandelbulb scenes).  The others are compiled without the first
+// wave and without the cost record: a second source for the loop's queue position alone took the Cornell kernel from 72
+// to 80 registers (7 → 6 resident CTAs, +4 %), and they have nothing to gain from an order.
+template <bool PLACED>
+__device__ __forceinline__ unsigned first_item(const FrameSync &S, int lane)
+{
+    if (PLACED && S.first_wave != 0u) return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    return claim_item(S, lane);
 }
 
 // kernel epilogue, reached by every thread of the CTA: when this was the grid's last CTA, all of the grid's stores

@@ -150,17 +150,12 @@ julia_kernel(const JuliaParams P)
     const f2 ji = F2(P.julia_i);
     unsigned iters = 0, samples = 0;
 
-    ItemBatch batch;
-    for (;;) {
-        // ---- one work item (frame_sync.cuh: claimed singly from a local queue, in guided batches from a shared one) ----
-        const unsigned qpos = next_item(P.sync, batch, (unsigned)P.n_items, lane);
-        if (qpos >= (unsigned)P.n_items) break;
-        const unsigned item = ordered_item(P.sync, qpos);                              // work order (frame_sync.cuh)
-        const unsigned item_t0 = item_clock();
+    // ---- one work item per trip (frame_sync.cuh: the first one by the warp's place in the grid, the others claimed singly) ----
+    for (unsigned item = first_item<false>(P.sync, lane); item < (unsigned)P.n_items; item = claim_item(P.sync, lane)) {
         // item → (band of this rank, block row inside the band, block column)
         const int per_band = P.blocks_x * P.blocks_y;
         const unsigned fi = frame_item(P.sync, item);                                  // interleaved multi-GPU deal (frame_sync.cuh)
-        if (fi >= P.sync.items_total) { record_item(P.sync, item, item_t0, lane); continue; }
+        if (fi >= P.sync.items_total) continue;
         const int fitem = (int)fi;
         const int band_k = fitem / per_band, in_band = fitem - band_k * per_band;
         const int by = in_band / P.blocks_x, bx = in_band - by * P.blocks_x;
@@ -263,7 +258,6 @@ julia_kernel(const JuliaParams P)
             }
         }
         __syncwarp();
-        record_item(P.sync, item, item_t0, lane);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -680,7 +680,7 @@ static int order_min_items()
 static bool order_attach(rmdf_ctx *ctx, const int key[24], int n_items, FrameSync *fs)
 {
     fs->order = nullptr; fs->rec = nullptr; fs->counts = nullptr;
-    if (!ctx->order_mode || fs->queue_sys || fs->batch_max > 1u || n_items < order_min_items()) return false;
+    if (!ctx->order_mode || fs->queue_sys || n_items < order_min_items()) return false;
     if (ctx->order_cap < (size_t)n_items) {
         // cudaFree waits for the device: no frame that still uses the old buffers is in flight afterwards
         if (ctx->d_order) { cudaFree(ctx->d_order); ctx->d_order = nullptr; }
@@ -851,7 +851,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     mp.cornell = ctx->d_cornell;
     mp.out = fb_dev;
     mp.sync.queue = ctx->d_queue; mp.sync.done = ctx->d_queue + 1;
-    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0; mp.sync.batch_max = 1; mp.sync.batch_div = 1;
+    mp.sync.signal = nullptr; mp.sync.signal_value = 0; mp.sync.queue_sys = 0;
     mp.sync.item_stride = 1; mp.sync.item_offset = 0; mp.sync.item_group = 1; mp.sync.items_total = 0;
     int world = 1;
     unsigned int *go_word = nullptr;
@@ -923,20 +923,16 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
         mp.sync.item_rotate = getenv("RMDF_NO_DEAL_ROTATE") ? 0u : 1u;
         mp.n_items = (int)(mine * g);
     }
-    if (const char *e = getenv("RMDF_BATCH_MAX")) {         // tuning override (experiments only)
-        const int v = atoi(e);
-        if (v >= 1 && v <= 64) { mp.sync.batch_max = (unsigned)v; mp.sync.batch_div = 4u * (unsigned)resident_warps; }
-    }
     if (mp.n_items == 0 && mp.sync.signal == nullptr) return RMDF_OK;
     const int okey[24] = { 1, p->scene, p->fb_w, p->fb_h, wl.rect_mode, wl.tile_x0, wl.tile_y0, wl.tile_w, wl.tile_h, wl.n_tiles,
                            p->shard_count, p->shard_rank, wl.shard_skew, wl.shard_ty0, mp.item_w, mp.item_h, mp.n_items,
                            (int)mp.sync.item_stride, (int)mp.sync.item_offset, (int)mp.sync.item_group, p->resolve_log2, p->flags, (int)mp.sync.item_rotate, 0 };
     // work order: the fractals have the heavy-tailed item costs it pays for (measured: config 4 −0.35 %, one GPU's eighth of it
     // −2.5 %, general power −5 %, config 1 −1…4 %); the Cornell box gains nothing and the CSG scene loses the 10 µs it costs
-    static const bool order_all = getenv("RMDF_ORDER_ALL") != nullptr;
+    // (the other scenes' kernels are compiled without it: march_kernel kOrdered)
     // (a frame drawn as the reference's 64 tiles cycles through 64 work lists: nothing to learn from the call before)
-    const bool ordered = (p->scene == RMDF_SCENE_MB_POWER8 || p->scene == RMDF_SCENE_MB_GENERAL || order_all) && wl.rect_mode != 1 &&
-                         order_attach(ctx, okey, mp.n_items, &mp.sync);
+    const bool placed = (p->scene == RMDF_SCENE_MB_POWER8 || p->scene == RMDF_SCENE_MB_GENERAL);
+    const bool ordered = placed && wl.rect_mode != 1 && order_attach(ctx, okey, mp.n_items, &mp.sync);
     if (!ordered) { mp.sync.order = nullptr; mp.sync.rec = nullptr; mp.sync.counts = nullptr; }
     int grid = ctas_per_sm * ctx->sm_count;
     // A frame of very few items is bound by the latency of its slowest one (config 1: one 8×4 tile marches for 80 of the
@@ -952,7 +948,7 @@ extern "C" int rmdf_render_device(rmdf_ctx *ctx, const rmdf_params *p, void *fb_
     }
     const int need = (mp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need > 0 ? need : 1;             // a rank without items still publishes its arrival flag
-    mp.sync.first_wave = (mp.sync.queue_sys || mp.sync.batch_max > 1u || getenv("RMDF_NO_FIRST_WAVE")) ? 0u : (unsigned)(grid * kWarpsPerCta);
+    mp.sync.first_wave = (!placed || mp.sync.queue_sys || getenv("RMDF_NO_FIRST_WAVE")) ? 0u : (unsigned)(grid * kWarpsPerCta);
 
     if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go" (see rmdf_frame_begin)
         cudaError_t ew = launch_wait_flags(go_word, 1, mp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
@@ -1059,7 +1055,7 @@ static int julia_params(rmdf_ctx *ctx, int w, int h, int smooth, double tick, in
     jp->n_items = (int)n;
     jp->out_stride = w >> k;
     jp->sync.queue = ctx->d_queue; jp->sync.done = ctx->d_queue + 1;
-    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0; jp->sync.batch_max = 1; jp->sync.batch_div = 1;
+    jp->sync.signal = nullptr; jp->sync.signal_value = 0; jp->sync.queue_sys = 0;
     jp->sync.item_stride = 1; jp->sync.item_offset = 0; jp->sync.item_group = 1; jp->sync.items_total = 0;
     jp->counters = ctx->d_counters;
     return RMDF_OK;
@@ -1092,15 +1088,11 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
         ctx->sync_ctrl = nullptr;
     }
     if (jp.n_items == 0 && jp.sync.signal == nullptr) return RMDF_OK;
-    const int okey[24] = { 2, jp.w, jp.h, jp.y0, jp.y1, jp.resolve_log2, jp.frame_layout, jp.band_h, jp.shard_rank, jp.shard_count,
-                           jp.item_h, jp.blocks_x, jp.blocks_y, jp.n_items, (int)jp.sync.item_stride, (int)jp.sync.item_offset,
-                           (int)jp.sync.item_group, 0, 0, 0, 0, 0, 0, 0 };
-    const bool ordered = (getenv("RMDF_ORDER_JULIA") != nullptr) && order_attach(ctx, okey, jp.n_items, &jp.sync);
-    if (!ordered) { jp.sync.order = nullptr; jp.sync.rec = nullptr; jp.sync.counts = nullptr; }
+    jp.sync.order = nullptr; jp.sync.rec = nullptr; jp.sync.counts = nullptr;   // no work order: 2 M cheap items, an order costs 3 % (profiles/r2_work_order.md)
     int grid = julia_ctas_per_sm() * ctx->sm_count;
     const int need = (jp.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need > 0 ? need : 1;
-    jp.sync.first_wave = (jp.sync.queue_sys || jp.sync.batch_max > 1u || getenv("RMDF_NO_FIRST_WAVE")) ? 0u : (unsigned)(grid * kWarpsPerCta);
+    jp.sync.first_wave = 0u;
     if (go_word && ctx->sync_rank != 0) {                  // rank != 0 of a multi-GPU frame: wait for rank 0's "go"
         cudaError_t ew = launch_wait_flags(go_word, 1, jp.sync.signal_value, (unsigned)ctx->sync_timeout_ms,
                                            ctx->d_queue + 2, ctx->stream);
@@ -1112,7 +1104,6 @@ static int julia_launch(rmdf_ctx *ctx, JuliaParams &jp, void *fb_dev)
     cudaError_t e = launch_julia(jp, grid, ctx->stream);
     if (e != cudaSuccess) return fail(RMDF_ERR_CUDA, "julia kernel launch: %s", cudaGetErrorString(e));
     ctx->launches++;
-    if (ordered) { int rc = order_finish(ctx, jp.sync, jp.n_items); if (rc) return rc; }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->ev_valid = true;
     return RMDF_OK;
