@@ -1,7 +1,7 @@
 """Work order (frame_sync.cuh) measured with the permutation made on the HOST (RMDF_ORDER_DEBUG=1: the library records
 item costs and leaves the order alone; rmdf_debug_order_get/_set move them): what the ordered queue is worth before
 any device-side sort exists.  Kernel ms (library events), L2 flushed, median of 9.
-    RMDF_ORDER_DEBUG=1 python profiles/exp_order.py [c4] [share] [c3] [c1] [julia]"""
+    RMDF_ORDER_DEBUG=1 python profiles/exp_order.py [c4] [share] [c3] [c1]"""
 import ctypes as C, json, os, sys, faulthandler
 sys.path.insert(0, ".")
 faulthandler.enable(); faulthandler.dump_traceback_later(500, exit=True)
@@ -108,6 +108,3 @@ if "c1" in what:          # needs RMDF_ORDER_MIN_ITEMS=1000 in the environment
     variants("c1_fast", lambda: sr.renderDevice(p1, ptr), orders=("identity", "octave_stable", "exact_desc"))
     p1p = sr.makeParams(2, None, 512, 512, 0.0, mode=R.MODE_PARITY)
     variants("c1_parity", lambda: sr.renderDevice(p1p, ptr), orders=("identity", "octave_stable", "exact_desc"))
-if "julia" in what:
-    os.environ["RMDF_ORDER_JULIA"] = "1"
-    variants("julia_plain", lambda: sr.juliaDevice(61440, 34560, 0, 7.0, (0, 34560), 3, jo.data_ptr()), orders=("identity", "octave_stable"))
