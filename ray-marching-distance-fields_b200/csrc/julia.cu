@@ -144,7 +144,8 @@ julia_kernel(const JuliaParams P)
     __syncthreads();
     const int mx = lane & 7, my = lane >> 3;        // a warp covers 16×4 samples: lane = 2 adjacent columns of one row
     const float kNaN = __int_as_float(0x7fffffff);
-    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    asm volatile("" : "+r"(lut_addr));              // opaque: stays in a register (ptxas re-derived the shared window base, 4 instructions, at every use)
     const int k = P.resolve_log2;
     const float log_2 = rg_log(2.0f), rcp_log_2 = 1.0f / log_2;
     const f2 ji = F2(P.julia_i);
@@ -162,6 +163,7 @@ julia_kernel(const JuliaParams P)
         const int band = band_k * P.shard_count + P.shard_rank;
         const int bw = min(kBlockDim, P.w - bx * kBlockDim), bh = min(P.item_h, P.band_h - by * P.item_h);
         const int X0 = bx * kBlockDim, Y0 = P.y0 + band * P.band_h + by * P.item_h;
+        if (lane == 0) samples += (unsigned)(bw * bh);                                 // every sample of the clipped block is rendered
 
         // x depends on the column only (Fractal2D.hs:82): the four column values of a lane are hoisted per block
         f2 xs[2];
@@ -210,8 +212,8 @@ julia_kernel(const JuliaParams P)
                     }
                 finished:
                     w0 = julia_word<SMOOTH>(it0, m0, log_2, rcp_log_2, lut_addr);
-                    iters += (unsigned)it0; samples++;
-                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, rcp_log_2, lut_addr); iters += (unsigned)it1; samples++; }
+                    iters += (unsigned)it0;
+                    if (live == 3u) { w1 = julia_word<SMOOTH>(it1, m1, log_2, rcp_log_2, lut_addr); iters += (unsigned)it1; }
                 }
                 if (live == 3u) *reinterpret_cast<uint2 *>(stage + ly * kBlockDim + lx) = make_uint2(w0, w1);
                 else if (live)  stage[ly * kBlockDim + lx] = w0;
