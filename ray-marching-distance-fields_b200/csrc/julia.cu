@@ -177,12 +177,14 @@ julia_kernel(const JuliaParams P)
             asm volatile("" : "+f"(xs[c].x), "+f"(xs[c].y));   // keep the values: without this ptxas re-does the IEEE divisions per sample
         }
 
+        int y_lane = Y0 + my;                                                          // this lane's row in the first tile row
+        asm volatile("" : "+r"(y_lane));             // keep it: ptxas otherwise redoes Y0 (three multiply-adds on reloaded parameters) in every tile row
 #pragma unroll 1
         for (int trow = 0; trow < (P.item_h >> 2); trow++) {
             const int ty = trow * 4;
             if (ty >= bh) break;
             const int ly = ty + my;
-            const float qy = KD ? div_known((float)(Y0 + ly), P.fh, P.rcp_fh) : (float)(Y0 + ly) / P.fh;
+            const float qy = KD ? div_known((float)(y_lane + ty), P.fh, P.rcp_fh) : (float)(y_lane + ty) / P.fh;
             const f2 ys = F2(qy * 2.9f - 1.45f);                                    // :81
 #pragma unroll
             for (int c = 0; c < 2; c++) {
