@@ -286,3 +286,39 @@ def test_reference_arm_threads_are_real(O):
     finally:
         os.environ.pop("OMP_NUM_THREADS", None)
     assert tn < t1 / 1.8, (t1, tn, cores)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/r2_bench_n{1,2,8}.json are the raw lines of `bench.py` runs on B200s (kept as evidence): each must be
+    the ONE JSON line of the driver's contract — metric, whole-job value, device-timed ms, roofline with its fraction,
+    the end-to-end leg with its copy sizes, kernel launches, clocks without thermal throttling — and consistent in itself."""
+    import json
+    for n in (1, 2, 8):
+        p = ROOT / "profiles" / ("r2_bench_n%d.json" % n)
+        line = json.loads(p.read_text().strip().splitlines()[-1])
+        assert line["metric"] == "mandelbulb_4k_samples_per_s" and line["unit"] == "samples/s" and line["n_gpus"] == n
+        assert line["higher_is_better"] is True and line["scaling"] == "strong" and line["dtype"] == "f32" and line["data"] == "synthetic"
+        assert line["steps"] >= 10 and line["warmup"] >= 3
+        samples = 15360 * 8640
+        assert abs(line["value"] - samples / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
+        assert line["config"]["fb"] == [15360, 8640] and line["config"]["spp"] == 16 and "workload" in line["config"]
+        r = line["roofline"]
+        assert r["bound"] == "fp32_fma" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert 0.3 < r["frac"] < 1.0 and r["kernel_ms"] <= line["ms_per_step"] * 1.01
+        e = line["e2e"]
+        assert e["h2d_bytes_per_step"] > 4_000_000 and e["d2h_bytes_per_step"] == 3840 * 2160 * 4
+        assert e["value"] < line["value"]                          # copies inside the timed region cost something
+        assert line["gpu_launches"] >= line["steps"]
+        c = line["clocks"]
+        assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert line["tolerance_check"]["pass"] is True and line["tolerance_check"]["linear_psnr_db"] >= 50.0
+        w = line["work_order"]
+        assert w["enabled"] is True and w["kernel_ms"] > 0 and w["scan_order_kernel_ms"] > 0
+        if n == 1:
+            assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+            assert line["parity_check"]["bit_identical"] is True and line["parity_check"]["samples_differing"] == 0
+            assert set(line["configs"]) >= {"config1_mandelbulb_512", "config2_prefilter", "config3_cornell_1080p_4spp",
+                                            "config3_csg_1080p_4spp", "config5_julia_8k_64spp", "mandelbulb_general_4k"}
+        else:
+            assert line["frame_equals_single_gpu"] is True and len(line["rank_kernel_ms"]) == n
+            assert line["julia_8k_64spp"]["frame_equals_single_gpu"] is True
